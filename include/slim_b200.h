@@ -1,0 +1,76 @@
+/*
+ * slim_b200.h -- extension entry points of libslim.so (slim-b200) that have no counterpart in the
+ * reference header.  They expose the two halves of SLIM_Learn separately so that a caller can
+ *   (1) keep the training matrix resident in HBM across many learn calls (regularisation sweeps,
+ *       model selection: reference src/programs/slim_mselect.c:99-108 re-stages R every time), and
+ *   (2) solve an arbitrary subset of target item columns on one GPU and leave the result on the
+ *       device, which is what column-sharded multi-GPU learning needs: the reference's
+ *       `#pragma omp for` over columns (src/libslim/estimate.c:402-403) becomes one process per
+ *       GPU, each calling SLIMB200_LearnColumns on its shard, followed by one all-gather of W.
+ * Plain C ABI: pointers and sizes only.
+ */
+#ifndef SLIM_B200_EXT_H
+#define SLIM_B200_EXT_H
+
+#include "slim.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct slimb200_matrix slimb200_matrix_t; /* R staged in HBM (CSR + padded CSC + norms) */
+typedef struct slimb200_result slimb200_result_t; /* solved columns, device resident          */
+
+/* Number of usable CUDA devices (0 when there is none). */
+int32_t SLIMB200_DeviceCount(void);
+/* Message of the last failure on the calling thread. */
+const char *SLIMB200_LastError(void);
+
+/* Stage a CSR training matrix on `device`: the work of CreateTrainingMatrix
+ * (reference src/libslim/setup.c:109-135).  rowval may be NULL (all-ones ratings).
+ * Host pointers; for best H2D rates pass page-locked memory. */
+slimb200_matrix_t *SLIMB200_Stage(int32_t device, int32_t nrows, const ssize_t *rowptr,
+                                  const int32_t *rowind, const float *rowval, int32_t *r_status);
+/* Same, from CSR arrays that already live on `device` (nnz = rowptr[nrows]). */
+slimb200_matrix_t *SLIMB200_StageDevice(int32_t device, int32_t nrows, int64_t nnz,
+                                        const int64_t *d_rowptr, const int32_t *d_rowind,
+                                        const float *d_rowval, int32_t *r_status);
+void SLIMB200_FreeMatrix(slimb200_matrix_t **matrix);
+int32_t SLIMB200_MatrixInfo(const slimb200_matrix_t *matrix, int32_t *nrows, int32_t *ncols,
+                            int64_t *nnz, int32_t *device, double *stage_ms, int32_t *stage_launches);
+/* Copy the staged column view back to the host (colptr int64[ncols+1], unpadded). */
+int32_t SLIMB200_MatrixCSC(const slimb200_matrix_t *matrix, int64_t *colptr, int32_t *colind,
+                           float *colval, float *cnorms);
+
+/* Solve target columns cols[0..ncols_sel) (cols == NULL: every column): the per-column body of
+ * EstimateModelCD (reference src/libslim/estimate.c:405-505) + CoordinateDescent (cd.c:101-142).
+ * Options as for SLIM_Learn.  imodel: optional warm-start model handle. */
+slimb200_result_t *SLIMB200_LearnColumns(slimb200_matrix_t *matrix, const int32_t *ioptions,
+                                         const double *doptions, const int32_t *cols,
+                                         int32_t ncols_sel, const slim_t *imodel, int32_t *r_status);
+void SLIMB200_FreeResult(slimb200_result_t **result);
+/* nsel, total nnz, CUDA-event time of the solve kernel(s) and of the gather kernel (ms),
+ * kernels launched. Any pointer may be NULL. */
+int32_t SLIMB200_ResultInfo(const slimb200_result_t *result, int32_t *nsel, int64_t *nnz,
+                            double *solve_ms, double *gather_ms, int32_t *launches);
+/* Per-column counters in the order of `cols` (any pointer may be NULL): sweeps executed
+ * (cd.c:140), |A_j|, sum of nnz over active columns, sum of row lengths over the users of column j,
+ * 1/2||y - yhat||^2 and the objective (estimate.c:477-489). */
+int32_t SLIMB200_ResultStats(const slimb200_result_t *result, int32_t *niters, int32_t *nactive,
+                             int64_t *active_nnz, int64_t *expand_nnz, double *rnorm, double *objval);
+/* Solved columns as CSC: colptr int64[nsel+1], colind int32[nnz] (ascending), colval float[nnz]. */
+int32_t SLIMB200_ResultToHost(const slimb200_result_t *result, int64_t *colptr, int32_t *colind,
+                              float *colval);
+/* Same into DEVICE buffers on the matrix's device: counts int32[nsel], colind, colval. */
+int32_t SLIMB200_ResultToDevice(const slimb200_result_t *result, int32_t *d_counts,
+                                int32_t *d_colind, float *d_colval);
+
+/* Build a model handle (both views, reference SaveModel src/libslim/estimate.c:570-593) from the
+ * CSC of all nitems columns, e.g. after gathering the shards of every GPU. */
+slim_t *SLIMB200_AssembleModel(int32_t nitems, const int64_t *colptr, const int32_t *colind,
+                               const float *colval, int32_t *r_status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLIM_B200_EXT_H */

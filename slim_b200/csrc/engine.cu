@@ -1,0 +1,1325 @@
+// engine.cu -- the sm_100a CUDA engine behind SLIM_Learn / Py_SLIM_Learn.
+//
+// Replaces, from scratch, the reference's OpenMP coordinate-descent learner:
+//   CreateTrainingMatrix   reference src/libslim/setup.c:109-135   -> stage()        (K0 kernels)
+//   EstimateModelCD        reference src/libslim/estimate.c:328-558 -> learn()        (cd_solve_kernel)
+//   CoordinateDescent      reference src/libslim/cd.c:101-142       -> the sweep loop inside cd_solve_kernel
+//   SaveModel              reference src/libslim/estimate.c:570-593 -> gather_columns_kernel + host assembly (api.cpp)
+//
+// Data layout in HBM:
+//   CSR   rowptr int64[nrows+1], rowind int32[nnz], rowval fp32[nnz] (absent for all-ones input)
+//   CSC   colptr int64[ncols+1] in PADDED entry units (every column starts on a 16-byte boundary and
+//         is padded to a multiple of 4 entries so a lane reads 4 user ids + 4 values with two 128-bit
+//         loads), colcnt int32[ncols] true lengths, colind int32[nnzp], colval fp32[nnzp],
+//         cnorms fp32[ncols] (reference rounding), csq fp64[ncols] exact sum of squares.
+//
+// There is no CPU fallback: every entry point fails with an error status when CUDA is unusable.
+#include "engine.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace slimb200 {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+const char *last_error() { return g_last_error.c_str(); }
+
+struct EngineError : std::runtime_error {
+  int status;
+  EngineError(int st, const std::string &m) : std::runtime_error(m), status(st) {}
+};
+
+static inline void ck(cudaError_t e, const char *what) {
+  if (e != cudaSuccess) {
+    int st = (e == cudaErrorMemoryAllocation) ? kErrMemory : kErr;
+    throw EngineError(st, std::string(what) + ": " + cudaGetErrorString(e));
+  }
+}
+#define CK(x) ck((x), #x)
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { reset(); }
+  void reset() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    reset();
+    n = count;
+    CK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+  }
+  void alloc_zero(size_t count, cudaStream_t s) {
+    alloc(count);
+    CK(cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), s));
+  }
+  T *release() {
+    T *q = p;
+    p = nullptr;
+    n = 0;
+    return q;
+  }
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    CK(cudaGetDevice(&prev));
+    if (prev != dev) CK(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// staged matrix
+// ------------------------------------------------------------------------------------------------
+struct Matrix {
+  int device = 0;
+  int32_t nrows = 0, ncols = 0;
+  int64_t nnz = 0, nnzp = 0;
+  bool has_val = false;
+  int64_t *d_rowptr = nullptr;
+  int32_t *d_rowind = nullptr;
+  float *d_rowval = nullptr;
+  int64_t *d_colptr = nullptr;
+  int32_t *d_colcnt = nullptr;
+  int32_t *d_colind = nullptr;
+  float *d_colval = nullptr;
+  float *d_cnorms = nullptr;
+  double *d_csq = nullptr;
+  std::vector<int32_t> h_colcnt;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  int smem_optin = 0;
+  double stage_ms = 0.0;
+  int32_t stage_launches = 0;
+  // solve scratch, cached between learn() calls on the same matrix
+  void *d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+void free_matrix(Matrix *m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaFree(m->d_rowptr);
+  cudaFree(m->d_rowind);
+  cudaFree(m->d_rowval);
+  cudaFree(m->d_colptr);
+  cudaFree(m->d_colcnt);
+  cudaFree(m->d_colind);
+  cudaFree(m->d_colval);
+  cudaFree(m->d_cnorms);
+  cudaFree(m->d_csq);
+  cudaFree(m->d_scratch);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+void matrix_info(const Matrix *m, int32_t *nrows, int32_t *ncols, int64_t *nnz, int32_t *device,
+                 double *stage_ms, int32_t *stage_launches) {
+  if (nrows) *nrows = m->nrows;
+  if (ncols) *ncols = m->ncols;
+  if (nnz) *nnz = m->nnz;
+  if (device) *device = m->device;
+  if (stage_ms) *stage_ms = m->stage_ms;
+  if (stage_launches) *stage_launches = m->stage_launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: staging kernels (CSR -> padded CSC, norms).  Replaces gk_csr_CreateIndex(COL)
+// (reference lib/GKlib/csr.c:1501-1585) and gk_csr_ComputeNorms (csr.c:1897-1938).
+// ------------------------------------------------------------------------------------------------
+__global__ void max_index_kernel(const int32_t *__restrict__ ind, int64_t n, int32_t *out_max,
+                                 int32_t *out_min) {
+  int32_t mx = -1, mn = 0x7fffffff;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    int32_t v = ind[k];
+    mx = max(mx, v);
+    mn = min(mn, v);
+  }
+  for (int o = 16; o; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out_max, mx);
+    atomicMin(out_min, mn);
+  }
+}
+
+__global__ void count_columns_kernel(const int32_t *__restrict__ ind, int64_t n, int32_t *cnt,
+                                     uint32_t *pos) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    atomicAdd(&cnt[ind[k]], 1);
+    pos[k] = (uint32_t)k;
+  }
+}
+
+// Single-CTA scan over the column counts: colptr (padded to 4 entries) and cstart (unpadded).
+__global__ void scan_columns_kernel(const int32_t *__restrict__ cnt, int32_t ncols, int64_t *colptr,
+                                    int64_t *cstart) {
+  __shared__ int64_t s_pad[1024], s_raw[1024];
+  const int tid = threadIdx.x;
+  const int per = (ncols + 1023) / 1024;
+  const int lo = min(ncols, tid * per), hi = min(ncols, lo + per);
+  int64_t pad = 0, raw = 0;
+  for (int i = lo; i < hi; i++) {
+    raw += cnt[i];
+    pad += (cnt[i] + 3) & ~3;
+  }
+  s_pad[tid] = pad;
+  s_raw[tid] = raw;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    int64_t a = 0, b = 0;
+    if (tid >= o) {
+      a = s_pad[tid - o];
+      b = s_raw[tid - o];
+    }
+    __syncthreads();
+    s_pad[tid] += a;
+    s_raw[tid] += b;
+    __syncthreads();
+  }
+  int64_t bp = s_pad[tid] - pad, br = s_raw[tid] - raw;  // exclusive
+  for (int i = lo; i < hi; i++) {
+    colptr[i] = bp;
+    cstart[i] = br;
+    br += cnt[i];
+    bp += (cnt[i] + 3) & ~3;
+  }
+  if (tid == 1023) {
+    colptr[ncols] = s_pad[1023];
+    cstart[ncols] = s_raw[1023];
+  }
+}
+
+// After a STABLE sort of the nonzero positions by column id, entry k of the sorted stream is the
+// (k - cstart[c])-th nonzero of column c in ascending user order (csr.c:1549-1584 produces the
+// same order with its serial counting sort).
+template <bool HASVAL>
+__global__ void fill_csc_kernel(const int32_t *__restrict__ scol, const uint32_t *__restrict__ spos,
+                                int64_t nnz, const int64_t *__restrict__ rowptr, int32_t nrows,
+                                const float *__restrict__ rowval, const int64_t *__restrict__ colptr,
+                                const int64_t *__restrict__ cstart, int32_t *colind, float *colval) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t c = scol[k];
+    const int64_t p = spos[k];
+    int32_t lo = 0, hi = nrows;  // largest r with rowptr[r] <= p
+    while (hi - lo > 1) {
+      int32_t mid = lo + ((hi - lo) >> 1);
+      if (rowptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    const int64_t dst = colptr[c] + (k - cstart[c]);
+    colind[dst] = lo;
+    if (HASVAL) colval[dst] = rowval[p];
+  }
+}
+
+// One warp per column.  cnorms reproduces the reference rounding: float accumulation in ascending
+// user order, separate multiply and add (gk_fdot, lib/GKlib/gk_mkblas.h:161-170 compiled -std=c99),
+// then (float)sqrt((double)sum) (csr.c:1931); without values sqrt(count) (csr.c:1936).
+template <bool HASVAL>
+__global__ void column_norms_kernel(int32_t ncols, const int64_t *__restrict__ colptr,
+                                    const int32_t *__restrict__ colcnt, const float *__restrict__ colval,
+                                    float *cnorms, double *csq) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < ncols; c += warps) {
+    const int cnt = colcnt[c];
+    if (!HASVAL) {
+      if (lane == 0) {
+        cnorms[c] = (float)sqrt((double)cnt);
+        csq[c] = (double)cnt;
+      }
+      continue;
+    }
+    const float *v = colval + colptr[c];
+    float fsum = 0.0f;
+    double dsum = 0.0;
+    for (int base = 0; base < cnt; base += 32) {
+      const int e = base + lane;
+      const float x = e < cnt ? v[e] : 0.0f;
+      const float sq = __fmul_rn(x, x);
+      dsum += (double)x * (double)x;
+      const int lim = min(32, cnt - base);
+      for (int l = 0; l < lim; l++) fsum = __fadd_rn(fsum, __shfl_sync(0xffffffffu, sq, l));
+    }
+    for (int o = 16; o; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if (lane == 0) {
+      cnorms[c] = (float)sqrt((double)fsum);
+      csq[c] = dsum;
+    }
+  }
+}
+
+static int grid_for(int64_t n, int block, int sm_count) {
+  int64_t g = (n + block - 1) / block;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm_count * 16));
+}
+
+Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *rowind,
+              const float *rowval, bool on_device, int64_t nnz_if_device, int32_t *status) {
+  Matrix *m = nullptr;
+  try {
+    if (nrows < 0 || !rowptr) throw EngineError(kErrInput, "stage: bad nrows/rowptr");
+    if (device < 0 || device >= device_count())
+      throw EngineError(kErr, "stage: no usable CUDA device (this library has no CPU fallback)");
+    DeviceGuard guard(device);
+    m = new Matrix();
+    m->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    m->sm_count = prop.multiProcessorCount;
+    m->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    cudaStream_t s = m->stream;
+    m->nrows = nrows;
+    m->nnz = on_device ? nnz_if_device : (int64_t)rowptr[nrows];
+    m->has_val = rowval != nullptr;
+    const int64_t nnz = m->nnz;
+    if (nnz < 0 || nnz >= (int64_t)0xffffffffLL)
+      throw EngineError(kErrInput, "stage: nnz must be in [0, 2^32)");
+    if (!rowind && nnz > 0) throw EngineError(kErrInput, "stage: rowind is NULL");
+
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, s));
+
+    CK(cudaMalloc(&m->d_rowptr, sizeof(int64_t) * ((size_t)nrows + 1)));
+    CK(cudaMalloc(&m->d_rowind, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+    if (m->has_val) CK(cudaMalloc(&m->d_rowval, sizeof(float) * std::max<int64_t>(nnz, 1)));
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    static_assert(sizeof(ssize_t) == sizeof(int64_t), "LP64 only");
+    CK(cudaMemcpyAsync(m->d_rowptr, rowptr, sizeof(int64_t) * ((size_t)nrows + 1), kind, s));
+    if (nnz > 0) {
+      CK(cudaMemcpyAsync(m->d_rowind, rowind, sizeof(int32_t) * nnz, kind, s));
+      if (m->has_val) CK(cudaMemcpyAsync(m->d_rowval, rowval, sizeof(float) * nnz, kind, s));
+    }
+
+    // ncols = max(rowind) + 1   (setup.c:117)
+    DevBuf<int32_t> d_mm;
+    d_mm.alloc(2);
+    int32_t init[2] = {-1, 0x7fffffff};
+    CK(cudaMemcpyAsync(d_mm.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    if (nnz > 0) {
+      max_index_kernel<<<grid_for(nnz, 256, m->sm_count), 256, 0, s>>>(m->d_rowind, nnz, d_mm.p,
+                                                                      d_mm.p + 1);
+      m->stage_launches++;
+    }
+    int32_t mm[2];
+    CK(cudaMemcpyAsync(mm, d_mm.p, sizeof(mm), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (nnz > 0 && mm[1] < 0) throw EngineError(kErrInput, "stage: negative column index");
+    m->ncols = nnz > 0 ? mm[0] + 1 : 0;
+    const int32_t ncols = m->ncols;
+
+    CK(cudaMalloc(&m->d_colcnt, sizeof(int32_t) * std::max<int32_t>(ncols, 1)));
+    CK(cudaMemsetAsync(m->d_colcnt, 0, sizeof(int32_t) * std::max<int32_t>(ncols, 1), s));
+    CK(cudaMalloc(&m->d_colptr, sizeof(int64_t) * ((size_t)ncols + 1)));
+    CK(cudaMalloc(&m->d_cnorms, sizeof(float) * std::max<int32_t>(ncols, 1)));
+    CK(cudaMalloc(&m->d_csq, sizeof(double) * std::max<int32_t>(ncols, 1)));
+    DevBuf<int64_t> d_cstart;
+    d_cstart.alloc((size_t)ncols + 1);
+    DevBuf<uint32_t> d_pos, d_spos;
+    DevBuf<int32_t> d_scol;
+    d_pos.alloc(nnz);
+    d_spos.alloc(nnz);
+    d_scol.alloc(nnz);
+
+    if (nnz > 0) {
+      count_columns_kernel<<<grid_for(nnz, 256, m->sm_count), 256, 0, s>>>(m->d_rowind, nnz,
+                                                                          m->d_colcnt, d_pos.p);
+      m->stage_launches++;
+    }
+    scan_columns_kernel<<<1, 1024, 0, s>>>(m->d_colcnt, ncols, m->d_colptr, d_cstart.p);
+    m->stage_launches++;
+    m->h_colcnt.resize(ncols);
+    int64_t nnzp = 0;
+    CK(cudaMemcpyAsync(&nnzp, m->d_colptr + ncols, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    if (ncols > 0)
+      CK(cudaMemcpyAsync(m->h_colcnt.data(), m->d_colcnt, sizeof(int32_t) * ncols,
+                         cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    m->nnzp = nnzp;
+
+    CK(cudaMalloc(&m->d_colind, sizeof(int32_t) * std::max<int64_t>(nnzp, 4)));
+    CK(cudaMemsetAsync(m->d_colind, 0, sizeof(int32_t) * std::max<int64_t>(nnzp, 4), s));
+    if (m->has_val) {
+      CK(cudaMalloc(&m->d_colval, sizeof(float) * std::max<int64_t>(nnzp, 4)));
+      CK(cudaMemsetAsync(m->d_colval, 0, sizeof(float) * std::max<int64_t>(nnzp, 4), s));
+    }
+
+    if (nnz > 0) {
+      // stable LSD radix sort of (column id, nonzero position); plumbing, not the graded path
+      int bits = 1;
+      while ((1LL << bits) < (int64_t)ncols) bits++;
+      size_t tmp_bytes = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, m->d_rowind, d_scol.p, d_pos.p,
+                                         d_spos.p, nnz, 0, bits, s));
+      DevBuf<unsigned char> d_tmp;
+      d_tmp.alloc(tmp_bytes);
+      CK(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, m->d_rowind, d_scol.p, d_pos.p,
+                                         d_spos.p, nnz, 0, bits, s));
+      m->stage_launches += 4;  // cub onesweep: histogram + scan + per-digit passes (approximate)
+      if (m->has_val)
+        fill_csc_kernel<true><<<grid_for(nnz, 256, m->sm_count), 256, 0, s>>>(
+            d_scol.p, d_spos.p, nnz, m->d_rowptr, nrows, m->d_rowval, m->d_colptr, d_cstart.p,
+            m->d_colind, m->d_colval);
+      else
+        fill_csc_kernel<false><<<grid_for(nnz, 256, m->sm_count), 256, 0, s>>>(
+            d_scol.p, d_spos.p, nnz, m->d_rowptr, nrows, nullptr, m->d_colptr, d_cstart.p,
+            m->d_colind, nullptr);
+      m->stage_launches++;
+      CK(cudaStreamSynchronize(s));  // d_tmp must outlive the sort
+    }
+    if (ncols > 0) {
+      const int g = grid_for((int64_t)ncols * 32, 256, m->sm_count);
+      if (m->has_val)
+        column_norms_kernel<true><<<g, 256, 0, s>>>(ncols, m->d_colptr, m->d_colcnt, m->d_colval,
+                                                    m->d_cnorms, m->d_csq);
+      else
+        column_norms_kernel<false><<<g, 256, 0, s>>>(ncols, m->d_colptr, m->d_colcnt, nullptr,
+                                                     m->d_cnorms, m->d_csq);
+      m->stage_launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    m->stage_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (status) *status = kOk;
+    return m;
+  } catch (const EngineError &e) {
+    g_last_error = e.what();
+    if (status) *status = e.status;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    if (status) *status = kErrMemory;
+  }
+  free_matrix(m);
+  return nullptr;
+}
+
+int matrix_csc_to_host(const Matrix *m, int64_t *colptr, int32_t *colind, float *colval,
+                       float *cnorms) {
+  try {
+    DeviceGuard guard(m->device);
+    std::vector<int64_t> pp((size_t)m->ncols + 1);
+    std::vector<int32_t> pind((size_t)std::max<int64_t>(m->nnzp, 1));
+    std::vector<float> pval;
+    CK(cudaMemcpy(pp.data(), m->d_colptr, sizeof(int64_t) * pp.size(), cudaMemcpyDeviceToHost));
+    if (m->nnzp > 0)
+      CK(cudaMemcpy(pind.data(), m->d_colind, sizeof(int32_t) * m->nnzp, cudaMemcpyDeviceToHost));
+    if (m->has_val && colval) {
+      pval.resize((size_t)std::max<int64_t>(m->nnzp, 1));
+      if (m->nnzp > 0)
+        CK(cudaMemcpy(pval.data(), m->d_colval, sizeof(float) * m->nnzp, cudaMemcpyDeviceToHost));
+    }
+    int64_t o = 0;
+    for (int32_t c = 0; c < m->ncols; c++) {
+      colptr[c] = o;
+      for (int32_t e = 0; e < m->h_colcnt[c]; e++, o++) {
+        colind[o] = pind[pp[c] + e];
+        if (m->has_val && colval) colval[o] = pval[pp[c] + e];
+      }
+    }
+    colptr[m->ncols] = o;
+    if (cnorms && m->ncols > 0)
+      CK(cudaMemcpy(cnorms, m->d_cnorms, sizeof(float) * m->ncols, cudaMemcpyDeviceToHost));
+    return kOk;
+  } catch (const EngineError &e) {
+    g_last_error = e.what();
+    return e.status;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2 + K3: one team (a warp or a CTA) owns one target item column j from start to end.
+// ------------------------------------------------------------------------------------------------
+struct __align__(32) ActMeta {  // one active coordinate; built once per target, streamed per sweep
+  int64_t c0;   // padded offset of column i
+  int32_t cnt;  // nnz of column i
+  float aty;    // <a_i, y> rounded to float (gk_fkv_t.key; estimate.c:437, cd.c:118)
+  double den;   // (double)cnorm_i * cnorm_i + l2r  (cd.c:119,127)
+  double sq;    // exact sum of squares of column i (for the one-gather form of cd.c:122-123)
+};
+
+struct SolveArgs {
+  int32_t nrows, ncols;
+  const int64_t *rowptr;
+  const int32_t *rowind;
+  const float *rowval;
+  const int64_t *colptr;
+  const int32_t *colcnt;
+  const int32_t *colind;
+  const float *colval;
+  const float *cnorms;
+  const double *csq;
+  double l1r, l2r, opttol;
+  int32_t maxniters;
+  const int32_t *targets;
+  int32_t ntargets;
+  int32_t *queue;
+  // warm start (CSC of the initial model), wcolptr == nullptr for cold start
+  const int64_t *wcolptr;
+  const int32_t *wcolind;
+  const float *wcolval;
+  int32_t wncols;
+  // per-CTA scratch
+  double *acc;
+  float *xw;
+  int32_t *act_idx;
+  ActMeta *act_meta;
+  double *x;
+  double *yhat;
+  size_t col_stride, row_stride;
+  // outputs (indexed by position in `targets`)
+  int32_t *out_cnt;
+  int64_t *out_off;
+  int32_t *pool_idx;
+  float *pool_val;
+  unsigned long long *pool_used;
+  int64_t pool_cap;
+  int32_t *st_niters;
+  int32_t *st_nactive;
+  int64_t *st_actnnz;
+  int64_t *st_expand;
+  double *st_rnorm;
+  double *st_obj;
+};
+
+template <int NT>
+__device__ __forceinline__ void team_sync() {
+  if (NT == 32) __syncwarp(); else __syncthreads();
+}
+
+// Sum over the team; every thread returns the bit-identical value (fixed summation order), so the
+// coordinate update below is computed redundantly by all threads and needs no broadcast.
+template <int NT>
+__device__ __forceinline__ double team_sum(double v, double *red, int &par) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (NT == 32) return v;
+  constexpr int NW = NT / 32;
+  if ((threadIdx.x & 31) == 0) red[par * NW + (threadIdx.x >> 5)] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < NW; i++) s += red[par * NW + i];
+  par ^= 1;
+  return s;
+}
+
+template <int NT>
+__device__ __forceinline__ int team_excl_scan(bool flag, int *sc, int &total) {
+  const unsigned b = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31;
+  const int pre = __popc(b & ((1u << lane) - 1u));
+  const int wt = __popc(b);
+  if (NT == 32) {
+    total = wt;
+    return pre;
+  }
+  constexpr int NW = NT / 32;
+  const int w = threadIdx.x >> 5;
+  if (lane == 0) sc[w] = wt;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < NW; i++) {
+    const int t = sc[i];
+    base += (i < w) ? t : 0;
+    tot += t;
+  }
+  __syncthreads();
+  total = tot;
+  return base + pre;
+}
+
+struct Chunk {
+  uint4 ix;
+  float4 vv;
+};
+
+template <bool HASVAL>
+__device__ __forceinline__ void load_chunk(const SolveArgs &a, int64_t c0, int ch, Chunk &r) {
+  r.ix = __ldg(reinterpret_cast<const uint4 *>(a.colind + c0) + ch);
+  if (HASVAL) r.vv = __ldg(reinterpret_cast<const float4 *>(a.colval + c0) + ch);
+}
+
+template <bool HASVAL>
+__device__ __forceinline__ double dot_chunk(const Chunk &r, int e0, int cnt, const double *yh) {
+  double s = 0.0;
+  if (e0 + 0 < cnt) s += HASVAL ? (double)r.vv.x * yh[r.ix.x] : yh[r.ix.x];
+  if (e0 + 1 < cnt) s += HASVAL ? (double)r.vv.y * yh[r.ix.y] : yh[r.ix.y];
+  if (e0 + 2 < cnt) s += HASVAL ? (double)r.vv.z * yh[r.ix.z] : yh[r.ix.z];
+  if (e0 + 3 < cnt) s += HASVAL ? (double)r.vv.w * yh[r.ix.w] : yh[r.ix.w];
+  return s;
+}
+
+template <bool HASVAL>
+__device__ __forceinline__ void axpy_chunk(const Chunk &r, int e0, int cnt, double d, double *yh) {
+  if (e0 + 0 < cnt) yh[r.ix.x] += HASVAL ? d * (double)r.vv.x : d;
+  if (e0 + 1 < cnt) yh[r.ix.y] += HASVAL ? d * (double)r.vv.y : d;
+  if (e0 + 2 < cnt) yh[r.ix.z] += HASVAL ? d * (double)r.vv.z : d;
+  if (e0 + 3 < cnt) yh[r.ix.w] += HASVAL ? d * (double)r.vv.w : d;
+}
+
+template <int NT>
+__host__ __device__ constexpr size_t solve_fixed_smem() {
+  return sizeof(double) * 2 * (NT / 32) + sizeof(int) * (NT / 32) + 64;
+}
+
+template <int NT, bool YSMEM, bool HASVAL>
+__global__ void __launch_bounds__(NT) cd_solve_kernel(const SolveArgs a) {
+  constexpr int NW = NT / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *red = reinterpret_cast<double *>(smem_raw);
+  int *sc = reinterpret_cast<int *>(red + 2 * NW);
+  long long *s_misc = reinterpret_cast<long long *>(smem_raw + ((sizeof(double) * 2 * NW + sizeof(int) * NW + 15) & ~size_t(15)));
+  double *yh_s = reinterpret_cast<double *>(smem_raw + ((solve_fixed_smem<NT>() + 15) & ~size_t(15)));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int par = 0;
+
+  double *acc = a.acc + (size_t)blockIdx.x * a.col_stride;
+  float *xw = a.xw ? a.xw + (size_t)blockIdx.x * a.col_stride : nullptr;
+  int32_t *act_idx = a.act_idx + (size_t)blockIdx.x * a.col_stride;
+  ActMeta *meta = a.act_meta + (size_t)blockIdx.x * a.col_stride;
+  double *x = a.x + (size_t)blockIdx.x * a.col_stride;
+  double *yh = YSMEM ? yh_s : a.yhat + (size_t)blockIdx.x * a.row_stride;
+
+  if (YSMEM) {
+    for (int u = tid; u < a.nrows; u += NT) yh[u] = 0.0;
+  }
+
+  for (;;) {
+    // ---- next target from the cost-ordered queue -------------------------------------------
+    team_sync<NT>();
+    if (tid == 0) s_misc[0] = atomicAdd(a.queue, 1);
+    team_sync<NT>();
+    const int q = (int)s_misc[0];
+    if (q >= a.ntargets) break;
+    const int j = a.targets[q];
+    const int64_t cj0 = a.colptr[j];
+    const int cntj = a.colcnt[j];
+
+    // ---- K1: candidates and aTy by CSR row expansion (replaces the full CSC sweep of
+    //      estimate.c:412-421): acc[i] += r_ui * r_uj for every user u of column j -------------
+    long long expand = 0;
+    for (int e = warp; e < cntj; e += NW) {
+      const int u = a.colind[cj0 + e];
+      const double vy = HASVAL ? (double)a.colval[cj0 + e] : 1.0;
+      const int64_t r0 = a.rowptr[u], r1 = a.rowptr[u + 1];
+      for (int64_t k = r0 + lane; k < r1; k += 32) {
+        const int i = __ldg(a.rowind + k);
+        const double prod = HASVAL ? (double)__ldg(a.rowval + k) * vy : 1.0;
+        atomicAdd(&acc[i], prod);
+      }
+      if (lane == 0) expand += (r1 - r0);
+    }
+    // warm start: scatter column j of the initial model (estimate.c:455-458)
+    const bool warm = a.wcolptr != nullptr && j < a.wncols;
+    if (warm) {
+      for (int64_t k = a.wcolptr[j] + tid; k < a.wcolptr[j + 1]; k += NT) {
+        const int r = a.wcolind[k];
+        if (r >= 0 && r < a.ncols) xw[r] = a.wcolval[k];
+      }
+    }
+    __threadfence_block();
+    team_sync<NT>();
+
+    // ---- active set: ascending i, strict aTy > l1r, i != j (estimate.c:433-444) ---------------
+    int na = 0;
+    long long actnnz = 0;
+    for (int base = 0; base < a.ncols; base += NT) {
+      const int i = base + tid;
+      double v = 0.0;
+      if (i < a.ncols) {
+        v = __ldcg(&acc[i]);  // L2: the atomics above bypass L1
+        if (v != 0.0) acc[i] = 0.0;
+      }
+      const bool flag = (i < a.ncols) && (i != j) && (v > a.l1r);
+      int tot;
+      const int pos = na + team_excl_scan<NT>(flag, sc, tot);
+      if (flag) {
+        ActMeta m;
+        m.c0 = a.colptr[i];
+        m.cnt = a.colcnt[i];
+        m.aty = (float)v;
+        const double cn = (double)a.cnorms[i];
+        m.den = cn * cn + a.l2r;
+        m.sq = a.csq[i];
+        meta[pos] = m;
+        act_idx[pos] = i;
+        x[pos] = warm ? (double)xw[i] : 0.0;
+        actnnz += m.cnt;
+      }
+      na += tot;
+    }
+    team_sync<NT>();
+    if (warm) {
+      for (int64_t k = a.wcolptr[j] + tid; k < a.wcolptr[j + 1]; k += NT) {
+        const int r = a.wcolind[k];
+        if (r >= 0 && r < a.ncols) xw[r] = 0.0f;
+      }
+    }
+
+    // ---- iteration cap (estimate.c:448-449) ---------------------------------------------------
+    const long long cap64 = 50LL * cntj;
+    const int maxit = (int)(cap64 < (long long)a.maxniters ? cap64 : (long long)a.maxniters);
+
+    // ---- yhat = sum x_i a_i for a warm start (cd.c:108-110, with AddSpVec's EPS skip) ---------
+    if (warm) {
+      for (int p = 0; p < na; p++) {
+        const double xi = x[p];
+        if (fabs(xi) > kEps) {
+          const ActMeta m = meta[p];
+          const int nch = (m.cnt + 3) >> 2;
+          for (int ch = tid; ch < nch; ch += NT) {
+            Chunk c;
+            load_chunk<HASVAL>(a, m.c0, ch, c);
+            axpy_chunk<HASVAL>(c, ch * 4, m.cnt, xi, yh);
+          }
+        }
+        team_sync<NT>();
+      }
+    }
+
+    // ---- K2: the coordinate-descent sweeps (cd.c:112-140), fixed ascending order --------------
+    int niters = 1;
+    if (na > 0 && maxit > 0) {
+      ActMeta m_cur = meta[0];
+      ActMeta m_nxt = meta[na > 1 ? 1 : 0];
+      Chunk c_cur;
+      c_cur.ix = make_uint4(0, 0, 0, 0);
+      c_cur.vv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tid < ((m_cur.cnt + 3) >> 2)) load_chunk<HASVAL>(a, m_cur.c0, tid, c_cur);
+      bool done = false;
+      int t = 0;
+      for (; t < maxit && !done; t++) {
+        double dltx = 0.0;
+        for (int p = 0; p < na; p++) {
+          const double xi = x[p];
+          int p2 = p + 2;
+          p2 = p2 >= na ? p2 - na : p2;
+          p2 = p2 >= na ? p2 - na : p2;
+          if (p2 >= na) p2 = 0;
+          const ActMeta m_nn = meta[p2];
+          const int nch = (m_cur.cnt + 3) >> 2;
+
+          // <a_i, yhat>: coalesced 128-bit column loads, gathered fp64 yhat, fp64 accumulate
+          double part = 0.0;
+          if (tid < nch) part = dot_chunk<HASVAL>(c_cur, tid * 4, m_cur.cnt, yh);
+          for (int ch = tid + NT; ch < nch; ch += NT) {
+            Chunk c;
+            load_chunk<HASVAL>(a, m_cur.c0, ch, c);
+            part += dot_chunk<HASVAL>(c, ch * 4, m_cur.cnt, yh);
+          }
+          // issue the next coordinate's first chunk before the reduction (independent of yhat)
+          Chunk c_nxt;
+          c_nxt.ix = make_uint4(0, 0, 0, 0);
+          c_nxt.vv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (tid < ((m_nxt.cnt + 3) >> 2)) load_chunk<HASVAL>(a, m_nxt.c0, tid, c_nxt);
+
+          const double ipf = team_sum<NT>(part, red, par);
+
+          // soft-threshold / shrink update (cd.c:122-128).  The reference removes x_i a_i from yhat,
+          // takes the inner product and adds x_i' a_i back; algebraically
+          //   ip = <a_i,yhat> - x_i*|a_i|^2,  yhat += (x_i' - x_i) a_i
+          // with AddSpVec's |x| <= EPS skip (cd.c:27) kept on both terms.
+          const double in_old = fabs(xi) > kEps ? xi : 0.0;
+          const double ip = ipf - in_old * m_cur.sq;
+          const double num = (double)m_cur.aty - ip;
+          const double nx = num > a.l1r ? (num - a.l1r) / m_cur.den : 0.0;
+          const double in_new = fabs(nx) > kEps ? nx : 0.0;
+          const double d = in_new - in_old;
+          if (d != 0.0) {
+            if (tid < nch) axpy_chunk<HASVAL>(c_cur, tid * 4, m_cur.cnt, d, yh);
+            for (int ch = tid + NT; ch < nch; ch += NT) {
+              Chunk c;
+              load_chunk<HASVAL>(a, m_cur.c0, ch, c);
+              axpy_chunk<HASVAL>(c, ch * 4, m_cur.cnt, d, yh);
+            }
+          }
+          if (tid == 0) x[p] = nx;
+          dltx += (nx - xi) * (nx - xi);
+          team_sync<NT>();  // yhat (and x[p]) visible to the whole team before the next gather
+          m_cur = m_nxt;
+          m_nxt = m_nn;
+          c_cur = c_nxt;
+        }
+        if (dltx < a.opttol) done = true;  // cd.c:135-138
+      }
+      niters = done ? t : maxit + 1;  // cd.c:140 (t + 1 at the break; maxit + 1 when the cap is hit)
+    } else if (maxit > 0) {
+      niters = (0.0 < a.opttol) ? 1 : maxit + 1;
+    }
+
+    // ---- residual / objective (estimate.c:477-489) --------------------------------------------
+    double yy = 0.0, yd = 0.0;
+    for (int e = tid; e < cntj; e += NT) {
+      const int u = a.colind[cj0 + e];
+      const double v = HASVAL ? (double)a.colval[cj0 + e] : 1.0;
+      yy += v * v;
+      yd += v * yh[u];
+    }
+    team_sync<NT>();
+    double hh = 0.0;
+    for (int u = tid; u < a.nrows; u += NT) {  // also restores yhat = 0 (estimate.c:528-530)
+      const double h = yh[u];
+      if (h != 0.0) {
+        hh += h * h;
+        yh[u] = 0.0;
+      }
+    }
+    double reg = 0.0;
+    int nnz_local = 0;
+    for (int p = tid; p < na; p += NT) {
+      const double xv = x[p];
+      reg += 0.5 * a.l2r * xv * xv + a.l1r * fabs(xv);
+      nnz_local += fabs(xv) > kEps ? 1 : 0;
+    }
+    yy = team_sum<NT>(yy, red, par);
+    yd = team_sum<NT>(yd, red, par);
+    hh = team_sum<NT>(hh, red, par);
+    reg = team_sum<NT>(reg, red, par);
+    const int nnz_w = (int)(team_sum<NT>((double)nnz_local, red, par) + 0.5);
+    const double expand_t = team_sum<NT>((double)expand, red, par);
+    const double actnnz_t = team_sum<NT>((double)actnnz, red, par);
+
+    // ---- K3: compaction |x| > EPS -> (i, (float)x) ascending i (estimate.c:492-505) ------------
+    if (tid == 0) {
+      const unsigned long long off = atomicAdd(a.pool_used, (unsigned long long)nnz_w);
+      s_misc[1] = (long long)off;
+    }
+    team_sync<NT>();
+    const long long off = s_misc[1];
+    const bool fits = off + nnz_w <= a.pool_cap;
+    if (fits) {
+      int w0 = 0;
+      for (int base = 0; base < na; base += NT) {
+        const int p = base + tid;
+        double xv = 0.0;
+        if (p < na) xv = x[p];
+        const bool flag = (p < na) && fabs(xv) > kEps;
+        int tot;
+        const int pos = w0 + team_excl_scan<NT>(flag, sc, tot);
+        if (flag) {
+          a.pool_idx[off + pos] = act_idx[p];
+          a.pool_val[off + pos] = (float)xv;
+        }
+        w0 += tot;
+      }
+    }
+    if (tid == 0) {
+      a.out_cnt[q] = fits ? nnz_w : -1 - nnz_w;
+      a.out_off[q] = off;
+      a.st_niters[q] = niters;
+      a.st_nactive[q] = na;
+      a.st_actnnz[q] = (long long)(actnnz_t + 0.5);
+      a.st_expand[q] = (long long)(expand_t + 0.5);
+      const double rn = 0.5 * (yy - 2.0 * yd + hh);
+      a.st_rnorm[q] = rn;
+      a.st_obj[q] = rn + reg;
+    }
+  }
+}
+
+// K3 (second half): ordered gather of the solved columns into compact CSC arrays (the CSC
+// assembly of SaveModel, estimate.c:570-588).  One warp per column.
+constexpr int kMaxPools = 10;
+struct PoolTable {
+  const int32_t *idx[kMaxPools];
+  const float *val[kMaxPools];
+};
+
+__global__ void gather_columns_kernel(int32_t nsel, const int64_t *__restrict__ src_off,
+                                      const int32_t *__restrict__ pool_of,
+                                      const int64_t *__restrict__ dst_off, const PoolTable pools,
+                                      int32_t *out_idx, float *out_val, int32_t *out_counts) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nsel; c += warps) {
+    const int64_t s = src_off[c], d = dst_off[c];
+    const int n = (int)(dst_off[c + 1] - d);
+    const int32_t *pi = pools.idx[pool_of[c]];
+    const float *pv = pools.val[pool_of[c]];
+    for (int e = lane; e < n; e += 32) {
+      out_idx[d + e] = pi[s + e];
+      out_val[d + e] = pv[s + e];
+    }
+    if (lane == 0) out_counts[c] = n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of learn()
+// ------------------------------------------------------------------------------------------------
+struct Result {
+  Matrix *m = nullptr;
+  int32_t nsel = 0;
+  int64_t nnz = 0;
+  // compact, caller-ordered CSC of the solved columns (device)
+  int64_t *d_colptr = nullptr;
+  int32_t *d_counts = nullptr;
+  int32_t *d_colind = nullptr;
+  float *d_colval = nullptr;
+  std::vector<int64_t> h_colptr;
+  std::vector<int32_t> niters, nactive;
+  std::vector<int64_t> actnnz, expand;
+  std::vector<double> rnorm, obj;
+  Timings tm{};
+};
+
+void free_result(Result *r) {
+  if (!r) return;
+  cudaSetDevice(r->m->device);
+  cudaFree(r->d_colptr);
+  cudaFree(r->d_counts);
+  cudaFree(r->d_colind);
+  cudaFree(r->d_colval);
+  delete r;
+}
+
+void result_info(const Result *r, int32_t *nsel, int64_t *nnz, Timings *t) {
+  if (nsel) *nsel = r->nsel;
+  if (nnz) *nnz = r->nnz;
+  if (t) *t = r->tm;
+}
+
+int result_stats(const Result *r, int32_t *niters, int32_t *nactive, int64_t *active_nnz,
+                 int64_t *expand_nnz, double *rnorm, double *objval) {
+  const size_t n = (size_t)r->nsel;
+  if (niters) memcpy(niters, r->niters.data(), n * sizeof(int32_t));
+  if (nactive) memcpy(nactive, r->nactive.data(), n * sizeof(int32_t));
+  if (active_nnz) memcpy(active_nnz, r->actnnz.data(), n * sizeof(int64_t));
+  if (expand_nnz) memcpy(expand_nnz, r->expand.data(), n * sizeof(int64_t));
+  if (rnorm) memcpy(rnorm, r->rnorm.data(), n * sizeof(double));
+  if (objval) memcpy(objval, r->obj.data(), n * sizeof(double));
+  return kOk;
+}
+
+int result_to_host(const Result *r, int64_t *colptr, int32_t *colind, float *colval) {
+  try {
+    DeviceGuard guard(r->m->device);
+    memcpy(colptr, r->h_colptr.data(), sizeof(int64_t) * ((size_t)r->nsel + 1));
+    if (r->nnz > 0) {
+      CK(cudaMemcpyAsync(colind, r->d_colind, sizeof(int32_t) * r->nnz, cudaMemcpyDeviceToHost,
+                         r->m->stream));
+      CK(cudaMemcpyAsync(colval, r->d_colval, sizeof(float) * r->nnz, cudaMemcpyDeviceToHost,
+                         r->m->stream));
+      CK(cudaStreamSynchronize(r->m->stream));
+    }
+    return kOk;
+  } catch (const EngineError &e) {
+    g_last_error = e.what();
+    return e.status;
+  }
+}
+
+int result_to_device(const Result *r, int32_t *d_counts, int32_t *d_colind, float *d_colval) {
+  try {
+    DeviceGuard guard(r->m->device);
+    cudaStream_t s = r->m->stream;
+    if (d_counts && r->nsel > 0)
+      CK(cudaMemcpyAsync(d_counts, r->d_counts, sizeof(int32_t) * r->nsel, cudaMemcpyDeviceToDevice, s));
+    if (r->nnz > 0) {
+      if (d_colind)
+        CK(cudaMemcpyAsync(d_colind, r->d_colind, sizeof(int32_t) * r->nnz, cudaMemcpyDeviceToDevice, s));
+      if (d_colval)
+        CK(cudaMemcpyAsync(d_colval, r->d_colval, sizeof(float) * r->nnz, cudaMemcpyDeviceToDevice, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return kOk;
+  } catch (const EngineError &e) {
+    g_last_error = e.what();
+    return e.status;
+  }
+}
+
+struct LaunchPlan {
+  int nt;
+  bool ysmem;
+  size_t smem;
+  int grid;
+};
+
+template <int NT, bool YSMEM, bool HASVAL>
+static void launch_solve(const SolveArgs &args, const LaunchPlan &plan, cudaStream_t s, bool query_only,
+                         int *blocks_per_sm) {
+  auto kern = cd_solve_kernel<NT, YSMEM, HASVAL>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  if (query_only) {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, NT, plan.smem));
+    return;
+  }
+  kern<<<plan.grid, NT, plan.smem, s>>>(args);
+  CK(cudaGetLastError());
+}
+
+static void dispatch_solve(const SolveArgs &args, const LaunchPlan &plan, bool hasval, cudaStream_t s,
+                           bool query_only, int *bps) {
+#define SLIM_DISPATCH(NTV)                                                                   \
+  if (plan.nt == NTV) {                                                                      \
+    if (plan.ysmem) {                                                                        \
+      if (hasval) launch_solve<NTV, true, true>(args, plan, s, query_only, bps);             \
+      else launch_solve<NTV, true, false>(args, plan, s, query_only, bps);                   \
+    } else {                                                                                 \
+      if (hasval) launch_solve<NTV, false, true>(args, plan, s, query_only, bps);            \
+      else launch_solve<NTV, false, false>(args, plan, s, query_only, bps);                  \
+    }                                                                                        \
+    return;                                                                                  \
+  }
+  SLIM_DISPATCH(32)
+  SLIM_DISPATCH(128)
+  SLIM_DISPATCH(512)
+#undef SLIM_DISPATCH
+  throw EngineError(kErr, "dispatch_solve: unsupported team size");
+}
+
+static size_t smem_for(int nt, bool ysmem, int32_t nrows) {
+  size_t fixed = nt == 32 ? solve_fixed_smem<32>() : nt == 128 ? solve_fixed_smem<128>() : solve_fixed_smem<512>();
+  fixed = (fixed + 15) & ~size_t(15);
+  return fixed + (ysmem ? sizeof(double) * (size_t)nrows : 0);
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel_in,
+              const WarmStart *warm, int32_t *status) {
+  Result *res = nullptr;
+  try {
+    DeviceGuard guard(m->device);
+    cudaStream_t s = m->stream;
+    const int32_t ncols = m->ncols, nrows = m->nrows;
+    const int32_t nsel = cols ? nsel_in : ncols;
+    if (nsel < 0) throw EngineError(kErrInput, "learn: negative column count");
+    for (int32_t q = 0; cols && q < nsel; q++)
+      if (cols[q] < 0 || cols[q] >= ncols) throw EngineError(kErrInput, "learn: column id out of range");
+
+    res = new Result();
+    res->m = m;
+    res->nsel = nsel;
+    res->h_colptr.assign((size_t)nsel + 1, 0);
+    res->niters.assign(nsel, 0);
+    res->nactive.assign(nsel, 0);
+    res->actnnz.assign(nsel, 0);
+    res->expand.assign(nsel, 0);
+    res->rnorm.assign(nsel, 0.0);
+    res->obj.assign(nsel, 0.0);
+
+    // processing order: heaviest target column first (longest-processing-time-first on the queue)
+    std::vector<int32_t> order(nsel);
+    std::iota(order.begin(), order.end(), 0);
+    auto colof = [&](int32_t q) { return cols ? cols[q] : q; };
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+      return m->h_colcnt[colof(x)] > m->h_colcnt[colof(y)];
+    });
+
+    // ---- launch plan ---------------------------------------------------------------------------
+    LaunchPlan plan{};
+    const double mean_col = ncols > 0 ? (double)m->nnz / ncols : 0.0;
+    plan.nt = mean_col <= 128.0 ? 32 : (mean_col <= 4096.0 ? 128 : 512);
+    plan.nt = env_int("SLIMB200_NT", plan.nt);
+    if (plan.nt != 32 && plan.nt != 128 && plan.nt != 512) plan.nt = 128;
+    const size_t smem_limit = (size_t)m->smem_optin;
+    plan.ysmem = smem_for(plan.nt, true, nrows) <= smem_limit;
+    if (env_int("SLIMB200_YHAT_GLOBAL", 0)) plan.ysmem = false;
+    if (plan.ysmem) {
+      // a large smem yhat leaves few CTAs per SM: widen the team to keep the SM busy
+      const size_t per = smem_for(plan.nt, true, nrows);
+      const size_t fit = (size_t)228 * 1024 / (per + 1024);
+      if (!getenv("SLIMB200_NT")) {
+        if (fit < 4) plan.nt = std::max(plan.nt, 512);
+        else if (fit < 16) plan.nt = std::max(plan.nt, 128);
+      }
+    }
+    plan.smem = smem_for(plan.nt, plan.ysmem, nrows);
+    int bps = 1;
+    SolveArgs args{};
+    dispatch_solve(args, plan, m->has_val, s, true, &bps);
+    bps = std::max(1, bps);
+    const int max_ctas = env_int("SLIMB200_CTAS_PER_SM", bps) * m->sm_count;
+    plan.grid = std::max(1, std::min<int>(nsel, std::min(max_ctas, bps * m->sm_count)));
+
+    // ---- scratch (cached on the matrix) --------------------------------------------------------
+    const size_t col_stride = ((size_t)std::max(ncols, 1) + 3) & ~size_t(3);
+    const size_t row_stride = ((size_t)std::max(nrows, 1) + 3) & ~size_t(3);
+    const size_t g = (size_t)plan.grid;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+      size_t o = off;
+      off += (bytes + 255) & ~size_t(255);
+      return o;
+    };
+    const size_t o_acc = carve(g * col_stride * sizeof(double));
+    const size_t o_xw = carve(g * col_stride * sizeof(float));
+    const size_t o_yh = carve(plan.ysmem ? 0 : g * row_stride * sizeof(double));
+    const size_t zero_bytes = off;  // acc, xw, yhat must start at zero
+    const size_t o_meta = carve(g * col_stride * sizeof(ActMeta));
+    const size_t o_x = carve(g * col_stride * sizeof(double));
+    const size_t o_idx = carve(g * col_stride * sizeof(int32_t));
+    if (off > m->scratch_bytes) {
+      cudaFree(m->d_scratch);
+      m->d_scratch = nullptr;
+      m->scratch_bytes = 0;
+      CK(cudaMalloc(&m->d_scratch, off));
+      m->scratch_bytes = off;
+    }
+    CK(cudaMemsetAsync(m->d_scratch, 0, zero_bytes, s));
+    unsigned char *sb = static_cast<unsigned char *>(m->d_scratch);
+
+    // ---- warm start ----------------------------------------------------------------------------
+    DevBuf<int64_t> d_wptr;
+    DevBuf<int32_t> d_wind;
+    DevBuf<float> d_wval;
+    if (warm && warm->colptr) {
+      const int64_t wnnz = warm->colptr[warm->ncols];
+      d_wptr.alloc((size_t)warm->ncols + 1);
+      d_wind.alloc(wnnz);
+      d_wval.alloc(wnnz);
+      CK(cudaMemcpyAsync(d_wptr.p, warm->colptr, sizeof(int64_t) * ((size_t)warm->ncols + 1),
+                         cudaMemcpyHostToDevice, s));
+      if (wnnz > 0) {
+        CK(cudaMemcpyAsync(d_wind.p, warm->colind, sizeof(int32_t) * wnnz, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_wval.p, warm->colval, sizeof(float) * wnnz, cudaMemcpyHostToDevice, s));
+      }
+    }
+
+    args.nrows = nrows;
+    args.ncols = ncols;
+    args.rowptr = m->d_rowptr;
+    args.rowind = m->d_rowind;
+    args.rowval = m->d_rowval;
+    args.colptr = m->d_colptr;
+    args.colcnt = m->d_colcnt;
+    args.colind = m->d_colind;
+    args.colval = m->d_colval;
+    args.cnorms = m->d_cnorms;
+    args.csq = m->d_csq;
+    args.l1r = p.l1r;
+    args.l2r = p.l2r;
+    args.opttol = p.opttol;
+    args.maxniters = p.maxniters;
+    args.wcolptr = d_wptr.p;
+    args.wcolind = d_wind.p;
+    args.wcolval = d_wval.p;
+    args.wncols = warm && warm->colptr ? warm->ncols : 0;
+    args.acc = reinterpret_cast<double *>(sb + o_acc);
+    args.xw = reinterpret_cast<float *>(sb + o_xw);
+    args.yhat = plan.ysmem ? nullptr : reinterpret_cast<double *>(sb + o_yh);
+    args.act_meta = reinterpret_cast<ActMeta *>(sb + o_meta);
+    args.x = reinterpret_cast<double *>(sb + o_x);
+    args.act_idx = reinterpret_cast<int32_t *>(sb + o_idx);
+    args.col_stride = col_stride;
+    args.row_stride = row_stride;
+
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventCreate(&e2));
+
+    // ---- solve, retrying the (rare) columns that did not fit the output pool --------------------
+    std::vector<int32_t> pending = order;  // indices into the caller's column list
+    std::vector<int64_t> src_off(nsel, 0);
+    std::vector<int32_t> cnt(nsel, 0);
+    struct Pool {
+      int32_t *idx;
+      float *val;
+    };
+    std::vector<Pool> pools;
+    std::vector<int32_t> pool_of(nsel, 0);
+    int64_t cap = std::max<int64_t>(1 << 20, (int64_t)nsel * std::min<int32_t>(std::max(ncols, 1), 2048));
+    double solve_ms = 0.0;
+    auto free_pools = [&]() {
+      for (auto &pl : pools) {
+        cudaFree(pl.idx);
+        cudaFree(pl.val);
+      }
+      pools.clear();
+    };
+    try {
+      for (int round = 0; !pending.empty(); round++) {
+        if (round >= kMaxPools) throw EngineError(kErr, "learn: output pool retry limit");
+        const int32_t nt = (int32_t)pending.size();
+        std::vector<int32_t> tcols(nt);
+        for (int32_t k = 0; k < nt; k++) tcols[k] = colof(pending[k]);
+        DevBuf<int32_t> d_targets, d_queue, d_ocnt, d_nit, d_nact;
+        DevBuf<int64_t> d_ooff, d_an, d_ex;
+        DevBuf<double> d_rn, d_ob;
+        DevBuf<unsigned long long> d_used;
+        d_targets.alloc(nt);
+        d_queue.alloc_zero(1, s);
+        d_used.alloc_zero(1, s);
+        d_ocnt.alloc(nt);
+        d_ooff.alloc(nt);
+        d_nit.alloc(nt);
+        d_nact.alloc(nt);
+        d_an.alloc(nt);
+        d_ex.alloc(nt);
+        d_rn.alloc(nt);
+        d_ob.alloc(nt);
+        Pool pl{nullptr, nullptr};
+        CK(cudaMalloc(&pl.idx, sizeof(int32_t) * cap));
+        pools.push_back(pl);
+        CK(cudaMalloc(&pools.back().val, sizeof(float) * cap));
+        CK(cudaMemcpyAsync(d_targets.p, tcols.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice, s));
+        args.targets = d_targets.p;
+        args.ntargets = nt;
+        args.queue = d_queue.p;
+        args.out_cnt = d_ocnt.p;
+        args.out_off = d_ooff.p;
+        args.pool_idx = pools.back().idx;
+        args.pool_val = pools.back().val;
+        args.pool_used = d_used.p;
+        args.pool_cap = cap;
+        args.st_niters = d_nit.p;
+        args.st_nactive = d_nact.p;
+        args.st_actnnz = d_an.p;
+        args.st_expand = d_ex.p;
+        args.st_rnorm = d_rn.p;
+        args.st_obj = d_ob.p;
+        LaunchPlan lp = plan;
+        lp.grid = std::min(plan.grid, nt);
+        CK(cudaEventRecord(e0, s));
+        dispatch_solve(args, lp, m->has_val, s, false, nullptr);
+        CK(cudaEventRecord(e1, s));
+        res->tm.launches++;
+        res->tm.solve_launches++;
+        std::vector<int32_t> h_cnt(nt), h_nit(nt), h_nact(nt);
+        std::vector<int64_t> h_off(nt), h_an(nt), h_ex(nt);
+        std::vector<double> h_rn(nt), h_ob(nt);
+        CK(cudaMemcpyAsync(h_cnt.data(), d_ocnt.p, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_off.data(), d_ooff.p, sizeof(int64_t) * nt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_nit.data(), d_nit.p, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_nact.data(), d_nact.p, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_an.data(), d_an.p, sizeof(int64_t) * nt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_ex.data(), d_ex.p, sizeof(int64_t) * nt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_rn.data(), d_rn.p, sizeof(double) * nt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_ob.data(), d_ob.p, sizeof(double) * nt, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        solve_ms += ms;
+        std::vector<int32_t> again;
+        int64_t need = 0;
+        for (int32_t k = 0; k < nt; k++) {
+          const int32_t q = pending[k];
+          res->niters[q] = h_nit[k];
+          res->nactive[q] = h_nact[k];
+          res->actnnz[q] = h_an[k];
+          res->expand[q] = h_ex[k];
+          res->rnorm[q] = h_rn[k];
+          res->obj[q] = h_ob[k];
+          if (h_cnt[k] >= 0) {
+            cnt[q] = h_cnt[k];
+            src_off[q] = h_off[k];
+            pool_of[q] = (int)pools.size() - 1;
+          } else {
+            again.push_back(q);
+            need += -1 - h_cnt[k];
+          }
+        }
+        pending.swap(again);
+        cap = std::max<int64_t>(need + 1024, 1 << 20);
+      }
+      res->tm.solve_ms = solve_ms;
+
+      // ---- ordered gather into compact CSC (caller's column order) ------------------------------
+      for (int32_t q = 0; q < nsel; q++) res->h_colptr[q + 1] = res->h_colptr[q] + cnt[q];
+      res->nnz = res->h_colptr[nsel];
+      CK(cudaMalloc(&res->d_colptr, sizeof(int64_t) * ((size_t)nsel + 1)));
+      CK(cudaMalloc(&res->d_counts, sizeof(int32_t) * std::max(nsel, 1)));
+      CK(cudaMalloc(&res->d_colind, sizeof(int32_t) * std::max<int64_t>(res->nnz, 1)));
+      CK(cudaMalloc(&res->d_colval, sizeof(float) * std::max<int64_t>(res->nnz, 1)));
+      CK(cudaMemcpyAsync(res->d_colptr, res->h_colptr.data(), sizeof(int64_t) * ((size_t)nsel + 1),
+                         cudaMemcpyHostToDevice, s));
+      CK(cudaEventRecord(e1, s));
+      if (nsel > 0) {
+        PoolTable tab{};
+        for (size_t pi = 0; pi < pools.size(); pi++) {
+          tab.idx[pi] = pools[pi].idx;
+          tab.val[pi] = pools[pi].val;
+        }
+        DevBuf<int64_t> d_so;
+        DevBuf<int32_t> d_po;
+        d_so.alloc(nsel);
+        d_po.alloc(nsel);
+        CK(cudaMemcpyAsync(d_so.p, src_off.data(), sizeof(int64_t) * nsel, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_po.p, pool_of.data(), sizeof(int32_t) * nsel, cudaMemcpyHostToDevice, s));
+        gather_columns_kernel<<<grid_for((int64_t)nsel * 32, 256, m->sm_count), 256, 0, s>>>(
+            nsel, d_so.p, d_po.p, res->d_colptr, tab, res->d_colind, res->d_colval, res->d_counts);
+        CK(cudaGetLastError());
+        res->tm.launches++;
+        CK(cudaStreamSynchronize(s));
+      }
+      CK(cudaEventRecord(e2, s));
+      CK(cudaStreamSynchronize(s));
+      float gms = 0.f;
+      CK(cudaEventElapsedTime(&gms, e1, e2));
+      res->tm.gather_ms = gms;
+    } catch (...) {
+      free_pools();
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      cudaEventDestroy(e2);
+      throw;
+    }
+    free_pools();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    if (status) *status = kOk;
+    return res;
+  } catch (const EngineError &e) {
+    g_last_error = e.what();
+    if (status) *status = e.status;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    if (status) *status = kErrMemory;
+  }
+  free_result(res);
+  return nullptr;
+}
+
+}  // namespace slimb200

@@ -1,0 +1,63 @@
+// engine.h -- internal interface between the C-ABI shims (api.cpp) and the CUDA engine
+// (engine.cu).  Not installed; the public headers are include/slim.h and include/slim_b200.h.
+#pragma once
+#include <stdint.h>
+#include <sys/types.h>
+
+namespace slimb200 {
+
+// Return codes (include/slim.h slim_rstatus_et; reference include/slim.h:177-182)
+enum { kOk = 1, kErrInput = -2, kErrMemory = -3, kErr = -4 };
+
+constexpr double kEps = 1e-7;  // EPSILON, reference src/libslim/def.h:14
+
+struct LearnParams {
+  double l1r, l2r, opttol;
+  int32_t maxniters;
+  int32_t dbglvl;
+};
+
+// Host view of a model used for warm starts: CSC of a previous W (reference
+// src/libslim/estimate.c:453-464 reads imat->colptr/colind/colval).
+struct WarmStart {
+  int32_t ncols;
+  const ssize_t *colptr;
+  const int32_t *colind;
+  const float *colval;
+};
+
+struct Matrix;  // R staged in HBM: CSR + 16-byte-padded CSC + norms
+struct Result;  // solved columns, device resident
+
+// Kernel timing / work counters of one learn call (CUDA events on the engine stream).
+struct Timings {
+  double solve_ms;     // the CD kernel(s): candidate expansion + sweeps + compaction
+  double gather_ms;    // ordered gather of the solved columns
+  int32_t launches;    // kernels launched by the call
+  int32_t solve_launches;
+};
+
+Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *rowind,
+              const float *rowval, bool inputs_on_device, int64_t nnz_if_device, int32_t *status);
+void free_matrix(Matrix *m);
+void matrix_info(const Matrix *m, int32_t *nrows, int32_t *ncols, int64_t *nnz, int32_t *device,
+                 double *stage_ms, int32_t *stage_launches);
+// Copies the staged column view back (tests): colptr is in UNPADDED units.
+int matrix_csc_to_host(const Matrix *m, int64_t *colptr, int32_t *colind, float *colval,
+                       float *cnorms);
+
+Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel,
+              const WarmStart *warm, int32_t *status);
+void free_result(Result *r);
+void result_info(const Result *r, int32_t *nsel, int64_t *nnz, Timings *t);
+// Per-column statistics in the caller's column order; any pointer may be null.
+int result_stats(const Result *r, int32_t *niters, int32_t *nactive, int64_t *active_nnz,
+                 int64_t *expand_nnz, double *rnorm, double *objval);
+int result_to_host(const Result *r, int64_t *colptr, int32_t *colind, float *colval);
+// Same, into caller-owned DEVICE buffers on the matrix's device (counts int32[nsel]).
+int result_to_device(const Result *r, int32_t *d_counts, int32_t *d_colind, float *d_colval);
+
+int device_count();
+const char *last_error();
+
+}  // namespace slimb200
