@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- item-columns solved per second of the SLIM coordinate-descent learn path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on): synthetic R, 1 M users x
+100 K items, 100 M nnz, Zipf(1.1) item popularity, all ratings 1.0 passed with a non-NULL value
+array (8 B per stored nonzero), l1r = l2r = 1, optTol 1e-7, niters 50.  The reference formulation
+costs O(nitems * nnz) (~0.5 GB streamed per sweep per target column), so a "step"
+solves a STRATIFIED SAMPLE of target columns (every k-th column in nnz-sorted order, a different
+comb offset each step); both arms use the same sampling rule.  R (1.2 GB CSR + 0.8 GB CSC) is far
+larger than the 126 MB L2, and consecutive steps solve different columns.
+
+ours      : R resident in HBM (staged once, outside the timed region) -> `value`;
+            `e2e` re-stages R from pinned host memory and reads W back inside the timed region,
+            through the C ABI (SLIMB200_Stage + SLIMB200_LearnColumns + SLIMB200_ResultToHost).
+reference : the UNMODIFIED reference OpenMP learner built into oracle/_ref (column-mask variant,
+            see oracle/Makefile), all host cores, timed by the library's own "Learn" timer.
+
+N > 1 (torchrun): every rank holds a replica of R, the step's columns are dealt across ranks, one
+NCCL all-gather assembles W at the end of every step (inside the timed region); weak scaling
+(columns per step grow with N).  One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (nusers, nitems, per_user)
+    "c4": (1_000_000, 100_000, 100),   # BASELINE.json configs[3]  (metric's configuration)
+    "c3": (1_000_000, 50_000, 50),     # BASELINE.json configs[2]
+    "probe": (20_000, 2_000, 50),      # SURVEY.md section 6 probe (quick checks)
+}
+PARAMS = dict(l1r=1.0, l2r=1.0, optTol=1e-7, niters=50)
+BYTES_PER_NNZ = 8  # int32 user id + fp32 value: the input is passed with a value array
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SLIM_BENCH_WORKLOAD", "c4"))
+    ap.add_argument("--cols-per-step", type=int, default=int(os.environ.get("SLIM_BENCH_COLS", "296")),
+                    help="target columns per step PER GPU")
+    ap.add_argument("--cpu-cols", type=int, default=int(os.environ.get("SLIM_BENCH_CPU_COLS", "0")),
+                    help="columns per reference step (0: one per host thread)")
+    ap.add_argument("--l1r", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
+
+
+def make_matrix(workload, device):
+    import torch
+
+    from slim_b200.synth import zipf_csr
+
+    nu, ni, pu = WORKLOADS[workload]
+    t0 = time.time()
+    rp, ri, rv = zipf_csr(nu, ni, pu, device=device)
+    if device != "cpu":
+        torch.cuda.synchronize()
+    return rp, ri, rv, time.time() - t0
+
+
+def algorithmic_bytes(colcnt, cols, stats, wnnz, maxniters):
+    """b*[c_j + sum_u len(row_u)] + T_j*b*sum_{i in A_j} c_i + 8*nnz(w_j)."""
+    cj = colcnt[cols].astype(np.int64)
+    cap = np.minimum(50 * cj, maxniters)
+    sweeps = np.minimum(stats["niters"].astype(np.int64), cap)
+    cand = BYTES_PER_NNZ * (cj + stats["expand_nnz"])
+    sweep = BYTES_PER_NNZ * sweeps * stats["active_nnz"]
+    return int(cand.sum()), int(sweep.sum()), 8 * int(wnnz), sweeps
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline leg
+# ------------------------------------------------------------------------------------------------
+def _capture_stdout(fn):
+    """Run fn() with C-level stdout redirected to a file; returns (result, text)."""
+    sys.stdout.flush()
+    libc = C.CDLL("libc.so.6")
+    libc.fflush(None)
+    saved = os.dup(1)
+    with tempfile.TemporaryFile("w+b") as tf:
+        os.dup2(tf.fileno(), 1)
+        try:
+            out = fn()
+        finally:
+            libc.fflush(None)
+            os.dup2(saved, 1)
+            os.close(saved)
+        tf.seek(0)
+        return out, tf.read().decode(errors="replace")
+
+
+def reference_step(ref, rp, ri, rv, cols, nthreads, l1r):
+    """One SLIM_Learn of the reference restricted to `cols` (mask exported by libslim_ref_cols.so).
+    Returns (seconds by the library's Learn timer, wall seconds, nnz of the solved columns)."""
+    import slimtest as st
+
+    ncols = int(ri.max()) + 1
+    mask = np.zeros(ncols, dtype=np.uint8)
+    mask[cols] = 1
+    C.c_void_p.in_dll(ref.lib, "slim_ref_colmask").value = mask.ctypes.data
+    io, do = st.options(l1r=l1r, l2r=PARAMS["l2r"], opttol=PARAMS["optTol"], niters=PARAMS["niters"],
+                        nthreads=nthreads, dbglvl=2)
+    t0 = time.time()
+    (h, status), text = _capture_stdout(lambda: ref.learn(rp, ri, rv, io, do))
+    wall = time.time() - t0
+    C.c_void_p.in_dll(ref.lib, "slim_ref_colmask").value = None
+    assert h and status == st.SLIM_OK
+    mv = st.model_views(h)
+    ref.free(h)
+    m = re.search(r"Learn:\s+([0-9.]+)", text)
+    learn_s = float(m.group(1)) if m else wall
+    return learn_s, wall, int(np.diff(mv["colptr"])[cols].sum())
+
+
+def run_reference(args, rp, ri, rv, colcnt, steps, warmup):
+    import slimtest as st
+
+    if not st.ref_lib_path(cols=True).exists():
+        return None
+    ref = st.load_ref(cols=True)
+    from slim_b200.synth import stratified_columns
+
+    nthreads = os.cpu_count() or 1
+    ncs = args.cpu_cols or nthreads
+    times, walls = [], []
+    for s in range(warmup + steps):
+        cols = stratified_columns(colcnt, ncs, offset=s)
+        learn_s, wall, _ = reference_step(ref, rp, ri, rv, cols, nthreads, args.l1r)
+        if s >= warmup:
+            times.append(learn_s)
+            walls.append(wall)
+    total = float(np.sum(times))
+    return dict(value=ncs * steps / total, cores=nthreads, cols_per_step=ncs, ms_per_step=1e3 * total / steps,
+                wall_ms_per_step=1e3 * float(np.mean(walls)))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    nu, ni, pu = WORKLOADS[args.workload]
+    wl_name = (f"synthetic R {nu} users x {ni} items, {nu * pu} nnz, Zipf(1.1), ratings 1.0 (fp32 values passed), "
+               f"l1r={args.l1r} l2r=1 optTol=1e-7 niters=50")
+    base = {"metric": "item-columns solved/sec (SLIM CD learn, stratified target-column sample)",
+            "unit": "columns/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import torch
+
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        rp, ri, rv, _ = make_matrix(args.workload, dev)
+        rp, ri, rv = rp.cpu().numpy(), ri.cpu().numpy(), rv.cpu().numpy()
+        colcnt = np.bincount(ri, minlength=int(ri.max()) + 1)
+        r = run_reference(args, rp, ri, rv, colcnt, args.steps, args.warmup)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libslim_ref_cols.so not built"}))
+            return 0
+        sample = (f"{r['cols_per_step']} stratified target columns per step, full R; timed by the reference's own "
+                  f"Learn timer (setup excluded)")
+        line = dict(base, impl="reference", value=r["value"], ms_per_step=r["ms_per_step"], n_gpus=args.gpus,
+                    config={"workload": wl_name, "cols_per_step": r["cols_per_step"], "l2_policy": "inputs >> L2"},
+                    cpu_baseline={"value": r["value"], "unit": "columns/s", "cores": r["cores"], "kind": "reference",
+                                  "sample": sample},
+                    e2e={"value": r["value"], "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- ours
+    import torch
+    import torch.distributed as dist
+
+    from slim_b200 import Staged, learn_columns
+    from slim_b200.dist import all_gather_columns, shard_columns
+    from slim_b200.synth import stratified_columns
+
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    rp_d, ri_d, rv_d, gen_s = make_matrix(args.workload, dev)
+    staged = Staged(rp_d, ri_d, rv_d, device=local_rank)   # inputs already resident in HBM
+    colcnt = np.diff(staged.csc()["colptr"]) if staged.nnz < 5_000_000 else \
+        torch.bincount(ri_d.to(torch.int64), minlength=staged.ncols).cpu().numpy()
+    params = dict(PARAMS, l1r=args.l1r)
+    ncs_total = args.cols_per_step * world
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(s, keep=None):
+        cols = stratified_columns(colcnt, ncs_total, offset=s)
+        mine = shard_columns(cols, colcnt, rank, world)
+        res = learn_columns(staged, params, cols=cols[mine])
+        if world > 1:
+            counts = torch.empty(max(res.nsel, 1), dtype=torch.int32, device=dev)
+            ind = torch.empty(max(res.nnz, 1), dtype=torch.int32, device=dev)
+            val = torch.empty(max(res.nnz, 1), dtype=torch.float32, device=dev)
+            res.to_device(counts, ind, val)
+            all_gather_columns(mine, counts[:res.nsel], ind[:res.nnz], val[:res.nnz], len(cols))
+        if keep is not None:
+            keep.append((cols[mine], res.stats(), res.nnz, res.solve_ms, res.launches))
+        res.close()
+
+    for s in range(args.warmup):
+        step(s)
+    sampler = ClockSampler(local_rank)
+    kept = []
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for s in range(args.steps):
+        step(args.warmup + s, kept)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    wall = float(tmax.item())
+    value = ncs_total * args.steps / wall
+
+    # roofline of the dominant kernel (cd_solve_kernel), from this rank's launches
+    cand_b = sweep_b = out_b = 0
+    solve_ms = 0.0
+    launches = 0
+    sweeps_all = []
+    for cols, stats, wnnz, sms, nl in kept:
+        cb, sb, ob, sw = algorithmic_bytes(colcnt, cols, stats, wnnz, PARAMS["niters"])
+        cand_b, sweep_b, out_b = cand_b + cb, sweep_b + sb, out_b + ob
+        solve_ms += sms
+        launches += nl
+        sweeps_all.append(sw)
+    peak, peak_src = measured_peak()
+    n_launch = max(len(kept), 1)
+    alg_per_launch = (cand_b + sweep_b + out_b) / n_launch
+    achieved = (cand_b + sweep_b + out_b) / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "cd_solve_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms_per_launch": solve_ms / n_launch,
+                "sweep_only_GBps": sweep_b / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0,
+                "mean_sweeps_per_column": float(np.mean(np.concatenate(sweeps_all))) if sweeps_all else 0.0}
+
+    # e2e: host buffers -> C ABI -> host result, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        rp_h = rp_d.cpu().pin_memory().numpy()
+        ri_h = ri_d.cpu().pin_memory().numpy()
+        rv_h = rv_d.cpu().pin_memory().numpy()
+        h2d = rp_h.nbytes + ri_h.nbytes + rv_h.nbytes
+        d2h_total = 0
+
+        def e2e_step(s):
+            nonlocal d2h_total
+            cols = stratified_columns(colcnt, ncs_total, offset=s)
+            mine = shard_columns(cols, colcnt, rank, world)
+            with Staged(rp_h, ri_h, rv_h, device=local_rank) as st_:
+                res = learn_columns(st_, params, cols=cols[mine])
+                w = res.to_host()
+                d2h_total += w["colptr"].nbytes + w["colind"].nbytes + w["colval"].nbytes
+                res.close()
+
+        e2e_step(0)
+        d2h_total = 0
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            e2e_step(args.warmup + s)
+        barrier()
+        ew = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ew, op=dist.ReduceOp.MAX)
+        e2e = {"value": ncs_total * args.steps / float(ew.item()), "unit": "columns/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_total / max(args.steps, 1)),
+               "api": "SLIMB200_Stage + SLIMB200_LearnColumns + SLIMB200_ResultToHost (host buffers)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            rp_h, ri_h, rv_h = rp_d.cpu().numpy(), ri_d.cpu().numpy(), rv_d.cpu().numpy()
+            r = run_reference(args, rp_h, ri_h, rv_h, colcnt, steps=1, warmup=0)
+            if r is not None:
+                cpu_baseline = {"value": r["value"], "unit": "columns/s", "cores": r["cores"], "kind": "reference",
+                                "sample": f"{r['cols_per_step']} stratified target columns of the same R, one "
+                                          f"SLIM_Learn of oracle/_ref (column-mask build), library Learn timer "
+                                          f"{r['ms_per_step'] / 1e3:.1f} s"}
+        except Exception as ex:  # the baseline leg must not take the bench line down
+            cpu_baseline = {"value": None, "unit": "columns/s", "cores": os.cpu_count(), "kind": "reference",
+                            "sample": f"failed: {ex!r}"}
+
+    if rank == 0:
+        line = dict(base, value=value, ms_per_step=1e3 * wall / args.steps,
+                    config={"workload": wl_name, "cols_per_step_per_gpu": args.cols_per_step,
+                            "parallelism": f"column-sharded x{world}, R replicated",
+                            "l2_policy": "inputs (2 GB CSR+CSC) >> 126 MB L2; different columns every step",
+                            "datagen_s": round(gen_s, 2), "stage_ms": round(staged.stage_ms, 2)},
+                    roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, clocks=clocks,
+                    gpu_launches=int(launches))
+        print(json.dumps(line))
+    staged.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -297,6 +297,7 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
     if (device < 0 || device >= device_count())
       throw EngineError(kErr, "stage: no usable CUDA device (this library has no CPU fallback)");
     DeviceGuard guard(device);
+    (void)cudaGetLastError();  // do not inherit a stale non-sticky error from the caller
     m = new Matrix();
     m->device = device;
     cudaDeviceProp prop;
@@ -893,7 +894,7 @@ __global__ void gather_columns_kernel(int32_t nsel, const int64_t *__restrict__ 
 // host side of learn()
 // ------------------------------------------------------------------------------------------------
 struct Result {
-  Matrix *m = nullptr;
+  int device = 0;  // a Result may outlive the Matrix it came from: it keeps no pointer to it
   int32_t nsel = 0;
   int64_t nnz = 0;
   // compact, caller-ordered CSC of the solved columns (device)
@@ -910,11 +911,14 @@ struct Result {
 
 void free_result(Result *r) {
   if (!r) return;
-  cudaSetDevice(r->m->device);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(r->device);
   cudaFree(r->d_colptr);
   cudaFree(r->d_counts);
   cudaFree(r->d_colind);
   cudaFree(r->d_colval);
+  if (prev >= 0) cudaSetDevice(prev);
   delete r;
 }
 
@@ -938,14 +942,11 @@ int result_stats(const Result *r, int32_t *niters, int32_t *nactive, int64_t *ac
 
 int result_to_host(const Result *r, int64_t *colptr, int32_t *colind, float *colval) {
   try {
-    DeviceGuard guard(r->m->device);
+    DeviceGuard guard(r->device);
     memcpy(colptr, r->h_colptr.data(), sizeof(int64_t) * ((size_t)r->nsel + 1));
-    if (r->nnz > 0) {
-      CK(cudaMemcpyAsync(colind, r->d_colind, sizeof(int32_t) * r->nnz, cudaMemcpyDeviceToHost,
-                         r->m->stream));
-      CK(cudaMemcpyAsync(colval, r->d_colval, sizeof(float) * r->nnz, cudaMemcpyDeviceToHost,
-                         r->m->stream));
-      CK(cudaStreamSynchronize(r->m->stream));
+    if (r->nnz > 0) {  // learn() synchronised its stream before returning: plain copies are safe
+      CK(cudaMemcpy(colind, r->d_colind, sizeof(int32_t) * r->nnz, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(colval, r->d_colval, sizeof(float) * r->nnz, cudaMemcpyDeviceToHost));
     }
     return kOk;
   } catch (const EngineError &e) {
@@ -956,17 +957,14 @@ int result_to_host(const Result *r, int64_t *colptr, int32_t *colind, float *col
 
 int result_to_device(const Result *r, int32_t *d_counts, int32_t *d_colind, float *d_colval) {
   try {
-    DeviceGuard guard(r->m->device);
-    cudaStream_t s = r->m->stream;
+    DeviceGuard guard(r->device);
     if (d_counts && r->nsel > 0)
-      CK(cudaMemcpyAsync(d_counts, r->d_counts, sizeof(int32_t) * r->nsel, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpy(d_counts, r->d_counts, sizeof(int32_t) * r->nsel, cudaMemcpyDeviceToDevice));
     if (r->nnz > 0) {
-      if (d_colind)
-        CK(cudaMemcpyAsync(d_colind, r->d_colind, sizeof(int32_t) * r->nnz, cudaMemcpyDeviceToDevice, s));
-      if (d_colval)
-        CK(cudaMemcpyAsync(d_colval, r->d_colval, sizeof(float) * r->nnz, cudaMemcpyDeviceToDevice, s));
+      if (d_colind) CK(cudaMemcpy(d_colind, r->d_colind, sizeof(int32_t) * r->nnz, cudaMemcpyDeviceToDevice));
+      if (d_colval) CK(cudaMemcpy(d_colval, r->d_colval, sizeof(float) * r->nnz, cudaMemcpyDeviceToDevice));
     }
-    CK(cudaStreamSynchronize(s));
+    CK(cudaDeviceSynchronize());
     return kOk;
   } catch (const EngineError &e) {
     g_last_error = e.what();
@@ -1030,6 +1028,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
   Result *res = nullptr;
   try {
     DeviceGuard guard(m->device);
+    (void)cudaGetLastError();
     cudaStream_t s = m->stream;
     const int32_t ncols = m->ncols, nrows = m->nrows;
     const int32_t nsel = cols ? nsel_in : ncols;
@@ -1038,7 +1037,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       if (cols[q] < 0 || cols[q] >= ncols) throw EngineError(kErrInput, "learn: column id out of range");
 
     res = new Result();
-    res->m = m;
+    res->device = m->device;
     res->nsel = nsel;
     res->h_colptr.assign((size_t)nsel + 1, 0);
     res->niters.assign(nsel, 0);
