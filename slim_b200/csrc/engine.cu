@@ -17,6 +17,7 @@
 #include "engine.h"
 
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include <algorithm>
 #include <cmath>
@@ -29,6 +30,8 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+
+namespace cg = cooperative_groups;
 
 namespace slimb200 {
 
@@ -105,7 +108,11 @@ struct Matrix {
   int device = 0;
   int32_t nrows = 0, ncols = 0;
   int64_t nnz = 0, nnzp = 0;
-  bool has_val = false;
+  bool has_val = false;   // the caller passed a value array
+  bool unit = false;      // ... and every stored value is exactly 1.0f: the kernels then skip the value
+                          // stream (4 B per nonzero instead of 8), same arithmetic as the binary path
+  int32_t rows_per_part = 0;      // user-range width of the 16-way column split (cluster kernel)
+  int32_t *d_colsplit = nullptr;  // [ncols][kParts+1] entry offsets of the user ranges in each column
   int64_t *d_rowptr = nullptr;
   int32_t *d_rowind = nullptr;
   float *d_rowval = nullptr;
@@ -138,6 +145,7 @@ void free_matrix(Matrix *m) {
   cudaFree(m->d_colval);
   cudaFree(m->d_cnorms);
   cudaFree(m->d_csq);
+  cudaFree(m->d_colsplit);
   cudaFree(m->d_scratch);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -284,6 +292,38 @@ __global__ void column_norms_kernel(int32_t ncols, const int64_t *__restrict__ c
   }
 }
 
+constexpr int kParts = 16;  // user ranges per column = largest cluster size
+
+__global__ void all_ones_kernel(const float *__restrict__ v, int64_t n, int32_t *not_one) {
+  bool bad = false;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x)
+    bad |= (v[k] != 1.0f);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(not_one, 1);
+}
+
+// colsplit[c][r] = number of entries of column c whose user id is < r * rows_per_part.  Users are
+// ascending inside a column, so CTA r of a cluster owns the contiguous entry range
+// [colsplit[c][r], colsplit[c][r+1]) and with it a private slice of yhat.
+__global__ void column_split_kernel(int32_t ncols, int32_t rows_per_part, const int64_t *__restrict__ colptr,
+                                    const int32_t *__restrict__ colcnt, const int32_t *__restrict__ colind,
+                                    int32_t *colsplit) {
+  const int64_t total = (int64_t)ncols * (kParts + 1);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t / (kParts + 1)), r = (int)(t % (kParts + 1));
+    const int cnt = colcnt[c];
+    const int32_t *ix = colind + colptr[c];
+    const int64_t bound = (int64_t)r * rows_per_part;
+    int lo = 0, hi = cnt;  // first entry with user >= bound
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)ix[mid] < bound) lo = mid + 1; else hi = mid;
+    }
+    colsplit[t] = lo;
+  }
+}
+
 static int grid_for(int64_t n, int block, int sm_count) {
   int64_t g = (n + block - 1) / block;
   return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm_count * 16));
@@ -416,6 +456,32 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
                                                      m->d_cnorms, m->d_csq);
       m->stage_launches++;
     }
+    // unit-valued input: drop the value streams on the device (after the norms were taken from them)
+    if (m->has_val && nnz > 0) {
+      DevBuf<int32_t> d_flag;
+      d_flag.alloc_zero(1, s);
+      all_ones_kernel<<<grid_for(nnz, 256, m->sm_count), 256, 0, s>>>(m->d_rowval, nnz, d_flag.p);
+      m->stage_launches++;
+      int32_t flag = 1;
+      CK(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      const bool keep = getenv("SLIMB200_KEEP_VALUES") && atoi(getenv("SLIMB200_KEEP_VALUES"));
+      if (flag == 0 && !keep) {
+        m->unit = true;
+        cudaFree(m->d_rowval);
+        cudaFree(m->d_colval);
+        m->d_rowval = nullptr;
+        m->d_colval = nullptr;
+      }
+    }
+    if (ncols > 0) {
+      m->rows_per_part = (nrows + kParts - 1) / kParts;
+      if (m->rows_per_part < 1) m->rows_per_part = 1;
+      CK(cudaMalloc(&m->d_colsplit, sizeof(int32_t) * (size_t)ncols * (kParts + 1)));
+      column_split_kernel<<<grid_for((int64_t)ncols * (kParts + 1), 256, m->sm_count), 256, 0, s>>>(
+          ncols, m->rows_per_part, m->d_colptr, m->d_colcnt, m->d_colind, m->d_colsplit);
+      m->stage_launches++;
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, s));
     CK(cudaStreamSynchronize(s));
@@ -448,8 +514,8 @@ int matrix_csc_to_host(const Matrix *m, int64_t *colptr, int32_t *colind, float 
     if (m->nnzp > 0)
       CK(cudaMemcpy(pind.data(), m->d_colind, sizeof(int32_t) * m->nnzp, cudaMemcpyDeviceToHost));
     if (m->has_val && colval) {
-      pval.resize((size_t)std::max<int64_t>(m->nnzp, 1));
-      if (m->nnzp > 0)
+      pval.assign((size_t)std::max<int64_t>(m->nnzp, 1), 1.0f);
+      if (m->nnzp > 0 && !m->unit)
         CK(cudaMemcpy(pval.data(), m->d_colval, sizeof(float) * m->nnzp, cudaMemcpyDeviceToHost));
     }
     int64_t o = 0;
@@ -863,6 +929,406 @@ __global__ void __launch_bounds__(NT) cd_solve_kernel(const SolveArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cluster variant for large user counts (yhat does not fit shared memory): one thread-block CLUSTER
+// owns one target column.  CTA r of the cluster owns the user range [r*U, (r+1)*U) -- for every
+// column that is a contiguous entry range (colsplit) -- and therefore a PRIVATE slice of yhat: the
+// gather and the update of a coordinate touch only that slice, so the only cross-CTA traffic per
+// coordinate is one partial inner product per CTA, exchanged through distributed shared memory with
+// a single cluster barrier.  The number of clusters in flight is capped so that all their yhat
+// vectors stay resident in the 126 MB L2 while the column streams come from HBM.
+// ------------------------------------------------------------------------------------------------
+struct __align__(128) ActMetaC {  // one active coordinate, one 128-byte line
+  int64_t c0;
+  int32_t cnt;
+  float aty;
+  double den;
+  double sq;
+  int32_t split[kParts + 1];
+  int32_t pad[7];
+};
+static_assert(sizeof(ActMetaC) == 128, "one line per active coordinate");
+
+struct ClusterArgs {
+  const int32_t *colsplit;
+  ActMetaC *meta;       // per cluster [col_stride]
+  double *xc;           // per CTA [col_stride]: every CTA keeps its own copy of x (identical values)
+  int32_t rows_per_part;
+};
+
+struct CoordView {  // what one CTA needs to know about one coordinate
+  int64_t c0;
+  int32_t s0, s1;  // this CTA's entry range inside the column
+  float aty;
+  double den, sq;
+};
+
+// The line was written by CTA 0 of the cluster: read it from L2 (ld.global.cg), never from this SM's L1.
+__device__ __forceinline__ CoordView load_view(const ActMetaC *m, int pr0, int pr1) {
+  CoordView v;
+  const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(m));      // c0, cnt, aty
+  const int4 h1 = __ldcg(reinterpret_cast<const int4 *>(m) + 1);  // den, sq
+  v.c0 = (int64_t)(((unsigned long long)(unsigned)h0.y << 32) | (unsigned)h0.x);
+  v.aty = __int_as_float(h0.w);
+  v.den = __hiloint2double(h1.y, h1.x);
+  v.sq = __hiloint2double(h1.w, h1.z);
+  v.s0 = __ldcg(&m->split[pr0]);
+  v.s1 = __ldcg(&m->split[pr1]);
+  return v;
+}
+
+template <bool HASVAL>
+__device__ __forceinline__ double dot_chunk_r(const Chunk &r, int e0, int lo, int hi, const double *yh) {
+  double s = 0.0;
+  if (e0 + 0 >= lo && e0 + 0 < hi) s += HASVAL ? (double)r.vv.x * yh[r.ix.x] : yh[r.ix.x];
+  if (e0 + 1 >= lo && e0 + 1 < hi) s += HASVAL ? (double)r.vv.y * yh[r.ix.y] : yh[r.ix.y];
+  if (e0 + 2 >= lo && e0 + 2 < hi) s += HASVAL ? (double)r.vv.z * yh[r.ix.z] : yh[r.ix.z];
+  if (e0 + 3 >= lo && e0 + 3 < hi) s += HASVAL ? (double)r.vv.w * yh[r.ix.w] : yh[r.ix.w];
+  return s;
+}
+
+template <bool HASVAL>
+__device__ __forceinline__ void axpy_chunk_r(const Chunk &r, int e0, int lo, int hi, double d, double *yh) {
+  if (e0 + 0 >= lo && e0 + 0 < hi) yh[r.ix.x] += HASVAL ? d * (double)r.vv.x : d;
+  if (e0 + 1 >= lo && e0 + 1 < hi) yh[r.ix.y] += HASVAL ? d * (double)r.vv.y : d;
+  if (e0 + 2 >= lo && e0 + 2 < hi) yh[r.ix.z] += HASVAL ? d * (double)r.vv.z : d;
+  if (e0 + 3 >= lo && e0 + 3 < hi) yh[r.ix.w] += HASVAL ? d * (double)r.vv.w : d;
+}
+
+constexpr int kClusterNT = 512;
+
+struct ClusterSmem {
+  double red[2][kClusterNT / 32];  // per-warp partials (double buffered)
+  double part[2][kParts];          // per-CTA partials of the whole cluster, written through DSMEM
+  int sc[kClusterNT / 32];
+  int q;
+  int na;
+  long long off;
+};
+
+// Sum over all threads of the cluster; every thread of every CTA returns the bit-identical value.
+__device__ __forceinline__ double cluster_sum(double v, ClusterSmem &sm, int &par, cg::cluster_group &cl,
+                                              int cs, int rank) {
+  constexpr int NW = kClusterNT / 32;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sm.red[par][threadIdx.x >> 5] = v;
+  __syncthreads();
+  if ((int)threadIdx.x < cs) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) s += sm.red[par][i];
+    double *dst = cl.map_shared_rank(&sm.part[par][rank], threadIdx.x);
+    *dst = s;
+  }
+  cl.sync();
+  double tot = 0.0;
+  for (int c = 0; c < cs; c++) tot += sm.part[par][c];
+  par ^= 1;
+  return tot;
+}
+
+template <bool HASVAL>
+__global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveArgs a, const ClusterArgs ca) {
+  constexpr int NT = kClusterNT, NW = NT / 32;
+  __shared__ ClusterSmem sm;
+  cg::cluster_group cl = cg::this_cluster();
+  const int cs = (int)cl.num_blocks();
+  const int rank = (int)cl.block_rank();
+  const int cid = blockIdx.x / cs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int par = 0;
+
+  const int pr0 = rank * (kParts / cs), pr1 = (rank + 1) * (kParts / cs);
+  const int64_t ulo64 = (int64_t)pr0 * ca.rows_per_part, uhi64 = (int64_t)pr1 * ca.rows_per_part;
+  const int u_lo = (int)(ulo64 < a.nrows ? ulo64 : a.nrows), u_hi = (int)(uhi64 < a.nrows ? uhi64 : a.nrows);
+
+  double *acc = a.acc + (size_t)cid * a.col_stride;
+  float *xw = a.xw + (size_t)cid * a.col_stride;
+  int32_t *act_idx = a.act_idx + (size_t)cid * a.col_stride;
+  ActMetaC *meta = ca.meta + (size_t)cid * a.col_stride;
+  double *x = ca.xc + (size_t)blockIdx.x * a.col_stride;
+  double *yh = a.yhat + (size_t)cid * a.row_stride;
+
+  for (;;) {
+    // ---- next target -----------------------------------------------------------------------------
+    if (rank == 0 && tid == 0) {
+      const int q = atomicAdd(a.queue, 1);
+      for (int c = 0; c < cs; c++) *cl.map_shared_rank(&sm.q, c) = q;
+    }
+    cl.sync();
+    const int q = sm.q;
+    if (q >= a.ntargets) break;
+    const int j = a.targets[q];
+    const int64_t cj0 = a.colptr[j];
+    const int cntj = a.colcnt[j];
+
+    // ---- K1: candidates / aTy by CSR row expansion, all warps of the cluster ------------------------
+    long long expand = 0;
+    for (int e = rank * NW + warp; e < cntj; e += cs * NW) {
+      const int u = a.colind[cj0 + e];
+      const double vy = HASVAL ? (double)a.colval[cj0 + e] : 1.0;
+      const int64_t r0 = a.rowptr[u], r1 = a.rowptr[u + 1];
+      for (int64_t k = r0 + lane; k < r1; k += 32) {
+        const int i = __ldg(a.rowind + k);
+        const double prod = HASVAL ? (double)__ldg(a.rowval + k) * vy : 1.0;
+        atomicAdd(&acc[i], prod);
+      }
+      if (lane == 0) expand += (r1 - r0);
+    }
+    const bool warm = a.wcolptr != nullptr && j < a.wncols;
+    if (warm && rank == 0) {
+      for (int64_t k = a.wcolptr[j] + tid; k < a.wcolptr[j + 1]; k += NT) {
+        const int r = a.wcolind[k];
+        if (r >= 0 && r < a.ncols) xw[r] = a.wcolval[k];
+      }
+    }
+    __threadfence();
+    cl.sync();
+
+    // ---- active set, built by CTA 0, read by all ----------------------------------------------------
+    long long actnnz = 0;
+    if (rank == 0) {
+      int na = 0;
+      for (int base = 0; base < a.ncols; base += NT) {
+        const int i = base + tid;
+        double v = 0.0;
+        if (i < a.ncols) {
+          v = __ldcg(&acc[i]);
+          if (v != 0.0) __stcg(&acc[i], 0.0);
+        }
+        const bool flag = (i < a.ncols) && (i != j) && (v > a.l1r);
+        int tot;
+        const int pos = na + team_excl_scan<NT>(flag, sm.sc, tot);
+        if (flag) {
+          ActMetaC m;
+          m.c0 = a.colptr[i];
+          m.cnt = a.colcnt[i];
+          m.aty = (float)v;
+          const double cn = (double)a.cnorms[i];
+          m.den = cn * cn + a.l2r;
+          m.sq = a.csq[i];
+          const int32_t *sp = ca.colsplit + (size_t)i * (kParts + 1);
+#pragma unroll
+          for (int k = 0; k <= kParts; k++) m.split[k] = sp[k];
+#pragma unroll
+          for (int k = 0; k < 7; k++) m.pad[k] = 0;
+          meta[pos] = m;
+          act_idx[pos] = i;
+          actnnz += m.cnt;
+        }
+        na += tot;
+      }
+      if (tid == 0)
+        for (int c = 0; c < cs; c++) *cl.map_shared_rank(&sm.na, c) = na;
+    }
+    __threadfence();
+    cl.sync();
+    const int na = sm.na;
+
+    // every CTA initialises its own copy of x (identical values everywhere)
+    for (int p = tid; p < na; p += NT) x[p] = warm ? (double)__ldcg(&xw[__ldcg(&act_idx[p])]) : 0.0;
+    __syncthreads();
+    cl.sync();  // all CTAs have read xw before CTA 0 clears it
+    if (warm && rank == 0) {
+      for (int64_t k = a.wcolptr[j] + tid; k < a.wcolptr[j + 1]; k += NT) {
+        const int r = a.wcolind[k];
+        if (r >= 0 && r < a.ncols) xw[r] = 0.0f;
+      }
+    }
+
+    const long long cap64 = 50LL * cntj;
+    const int maxit = (int)(cap64 < (long long)a.maxniters ? cap64 : (long long)a.maxniters);
+
+    // ---- warm start: yhat slice = sum x_i a_i over this CTA's user range ------------------------------
+    if (warm) {
+      for (int p = 0; p < na; p++) {
+        const double xi = x[p];
+        if (fabs(xi) > kEps) {
+          const CoordView v = load_view(&meta[p], pr0, pr1);
+          for (int ch = (v.s0 >> 2) + tid; ch < ((v.s1 + 3) >> 2); ch += NT) {
+            Chunk c;
+            load_chunk<HASVAL>(a, v.c0, ch, c);
+            axpy_chunk_r<HASVAL>(c, ch * 4, v.s0, v.s1, xi, yh);
+          }
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- K2: sweeps ---------------------------------------------------------------------------------
+    int niters = 1;
+    if (na > 0 && maxit > 0) {
+      CoordView v_cur = load_view(&meta[0], pr0, pr1);
+      CoordView v_nxt = load_view(&meta[na > 1 ? 1 : 0], pr0, pr1);
+      Chunk c_cur;
+      c_cur.ix = make_uint4(0, 0, 0, 0);
+      c_cur.vv = make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        const int ch = (v_cur.s0 >> 2) + tid;
+        if (ch < ((v_cur.s1 + 3) >> 2)) load_chunk<HASVAL>(a, v_cur.c0, ch, c_cur);
+      }
+      bool done = false;
+      int t = 0;
+      for (; t < maxit && !done; t++) {
+        double dltx = 0.0;
+        for (int p = 0; p < na; p++) {
+          const double xi = x[p];
+          int p2 = p + 2;
+          p2 = p2 >= na ? p2 - na : p2;
+          p2 = p2 >= na ? p2 - na : p2;
+          if (p2 >= na) p2 = 0;
+          const CoordView v_nn = load_view(&meta[p2], pr0, pr1);
+          const int ch0 = v_cur.s0 >> 2, ch1 = (v_cur.s1 + 3) >> 2;
+
+          double part = 0.0;
+          if (ch0 + tid < ch1) part = dot_chunk_r<HASVAL>(c_cur, (ch0 + tid) * 4, v_cur.s0, v_cur.s1, yh);
+          {
+            int ch = ch0 + tid + NT;
+            // 4 chunks in flight per thread: 4 x (16 B ids [+ 16 B values]) before the first gather
+            for (; ch + 3 * NT < ch1; ch += 4 * NT) {
+              Chunk c0, c1, c2, c3;
+              load_chunk<HASVAL>(a, v_cur.c0, ch, c0);
+              load_chunk<HASVAL>(a, v_cur.c0, ch + NT, c1);
+              load_chunk<HASVAL>(a, v_cur.c0, ch + 2 * NT, c2);
+              load_chunk<HASVAL>(a, v_cur.c0, ch + 3 * NT, c3);
+              part += dot_chunk_r<HASVAL>(c0, ch * 4, v_cur.s0, v_cur.s1, yh);
+              part += dot_chunk_r<HASVAL>(c1, (ch + NT) * 4, v_cur.s0, v_cur.s1, yh);
+              part += dot_chunk_r<HASVAL>(c2, (ch + 2 * NT) * 4, v_cur.s0, v_cur.s1, yh);
+              part += dot_chunk_r<HASVAL>(c3, (ch + 3 * NT) * 4, v_cur.s0, v_cur.s1, yh);
+            }
+            for (; ch < ch1; ch += NT) {
+              Chunk c;
+              load_chunk<HASVAL>(a, v_cur.c0, ch, c);
+              part += dot_chunk_r<HASVAL>(c, ch * 4, v_cur.s0, v_cur.s1, yh);
+            }
+          }
+          Chunk c_nxt;
+          c_nxt.ix = make_uint4(0, 0, 0, 0);
+          c_nxt.vv = make_float4(0.f, 0.f, 0.f, 0.f);
+          {
+            const int ch = (v_nxt.s0 >> 2) + tid;
+            if (ch < ((v_nxt.s1 + 3) >> 2)) load_chunk<HASVAL>(a, v_nxt.c0, ch, c_nxt);
+          }
+
+          const double ipf = cluster_sum(part, sm, par, cl, cs, rank);
+
+          const double in_old = fabs(xi) > kEps ? xi : 0.0;
+          const double ip = ipf - in_old * v_cur.sq;
+          const double num = (double)v_cur.aty - ip;
+          const double nx = num > a.l1r ? (num - a.l1r) / v_cur.den : 0.0;
+          const double in_new = fabs(nx) > kEps ? nx : 0.0;
+          const double d = in_new - in_old;
+          if (d != 0.0) {
+            if (ch0 + tid < ch1) axpy_chunk_r<HASVAL>(c_cur, (ch0 + tid) * 4, v_cur.s0, v_cur.s1, d, yh);
+            int ch = ch0 + tid + NT;
+            for (; ch + 3 * NT < ch1; ch += 4 * NT) {
+              Chunk c0, c1, c2, c3;
+              load_chunk<HASVAL>(a, v_cur.c0, ch, c0);
+              load_chunk<HASVAL>(a, v_cur.c0, ch + NT, c1);
+              load_chunk<HASVAL>(a, v_cur.c0, ch + 2 * NT, c2);
+              load_chunk<HASVAL>(a, v_cur.c0, ch + 3 * NT, c3);
+              axpy_chunk_r<HASVAL>(c0, ch * 4, v_cur.s0, v_cur.s1, d, yh);
+              axpy_chunk_r<HASVAL>(c1, (ch + NT) * 4, v_cur.s0, v_cur.s1, d, yh);
+              axpy_chunk_r<HASVAL>(c2, (ch + 2 * NT) * 4, v_cur.s0, v_cur.s1, d, yh);
+              axpy_chunk_r<HASVAL>(c3, (ch + 3 * NT) * 4, v_cur.s0, v_cur.s1, d, yh);
+            }
+            for (; ch < ch1; ch += NT) {
+              Chunk c;
+              load_chunk<HASVAL>(a, v_cur.c0, ch, c);
+              axpy_chunk_r<HASVAL>(c, ch * 4, v_cur.s0, v_cur.s1, d, yh);
+            }
+          }
+          if (tid == 0) x[p] = nx;
+          dltx += (nx - xi) * (nx - xi);
+          __syncthreads();  // this CTA's yhat slice and x[p] are private to the CTA: a CTA barrier is enough
+          v_cur = v_nxt;
+          v_nxt = v_nn;
+          c_cur = c_nxt;
+        }
+        if (dltx < a.opttol) done = true;
+      }
+      niters = done ? t : maxit + 1;
+    } else if (maxit > 0) {
+      niters = (0.0 < a.opttol) ? 1 : maxit + 1;
+    }
+
+    // ---- residual / objective over this CTA's user range, then cluster-reduced ------------------------
+    double yy = 0.0, yd = 0.0;
+    {
+      const int32_t *sp = ca.colsplit + (size_t)j * (kParts + 1);
+      const int s0 = sp[pr0], s1 = sp[pr1];
+      for (int e = s0 + tid; e < s1; e += NT) {
+        const int u = a.colind[cj0 + e];
+        const double v = HASVAL ? (double)a.colval[cj0 + e] : 1.0;
+        yy += v * v;
+        yd += v * yh[u];
+      }
+    }
+    __syncthreads();
+    double hh = 0.0;
+    for (int u = u_lo + tid; u < u_hi; u += NT) {
+      const double h = yh[u];
+      if (h != 0.0) {
+        hh += h * h;
+        yh[u] = 0.0;
+      }
+    }
+    double reg = 0.0;
+    int nnz_local = 0;
+    if (rank == 0) {
+      for (int p = tid; p < na; p += NT) {
+        const double xv = x[p];
+        reg += 0.5 * a.l2r * xv * xv + a.l1r * fabs(xv);
+        nnz_local += fabs(xv) > kEps ? 1 : 0;
+      }
+    }
+    yy = cluster_sum(yy, sm, par, cl, cs, rank);
+    yd = cluster_sum(yd, sm, par, cl, cs, rank);
+    hh = cluster_sum(hh, sm, par, cl, cs, rank);
+    reg = cluster_sum(reg, sm, par, cl, cs, rank);
+    const int nnz_w = (int)(cluster_sum((double)nnz_local, sm, par, cl, cs, rank) + 0.5);
+    const double expand_t = cluster_sum((double)expand, sm, par, cl, cs, rank);
+    const double actnnz_t = cluster_sum((double)actnnz, sm, par, cl, cs, rank);
+
+    // ---- K3: compaction by CTA 0 -----------------------------------------------------------------------
+    if (rank == 0) {
+      if (tid == 0) sm.off = (long long)atomicAdd(a.pool_used, (unsigned long long)nnz_w);
+      __syncthreads();
+      const long long off = sm.off;
+      const bool fits = off + nnz_w <= a.pool_cap;
+      if (fits) {
+        int w0 = 0;
+        for (int base = 0; base < na; base += NT) {
+          const int p = base + tid;
+          double xv = 0.0;
+          if (p < na) xv = x[p];
+          const bool flag = (p < na) && fabs(xv) > kEps;
+          int tot;
+          const int pos = w0 + team_excl_scan<NT>(flag, sm.sc, tot);
+          if (flag) {
+            a.pool_idx[off + pos] = act_idx[p];
+            a.pool_val[off + pos] = (float)xv;
+          }
+          w0 += tot;
+        }
+      }
+      if (tid == 0) {
+        a.out_cnt[q] = fits ? nnz_w : -1 - nnz_w;
+        a.out_off[q] = off;
+        a.st_niters[q] = niters;
+        a.st_nactive[q] = na;
+        a.st_actnnz[q] = (long long)(actnnz_t + 0.5);
+        a.st_expand[q] = (long long)(expand_t + 0.5);
+        const double rn = 0.5 * (yy - 2.0 * yd + hh);
+        a.st_rnorm[q] = rn;
+        a.st_obj[q] = rn + reg;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // K3 (second half): ordered gather of the solved columns into compact CSC arrays (the CSC
 // assembly of SaveModel, estimate.c:570-588).  One warp per column.
 constexpr int kMaxPools = 10;
@@ -1012,6 +1478,32 @@ static void dispatch_solve(const SolveArgs &args, const LaunchPlan &plan, bool h
   throw EngineError(kErr, "dispatch_solve: unsupported team size");
 }
 
+template <bool HASVAL>
+static int cluster_launch(const SolveArgs &args, const ClusterArgs &cargs, int cs, int nclusters, cudaStream_t s,
+                          bool query_only) {
+  auto kern = cd_cluster_kernel<HASVAL>;
+  if (cs > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)(cs * std::max(nclusters, 1)), 1, 1);
+  cfg.blockDim = dim3(kClusterNT, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (query_only) {
+    int n = 0;
+    CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    return n;
+  }
+  CK(cudaLaunchKernelEx(&cfg, kern, args, cargs));
+  return 0;
+}
+
 static size_t smem_for(int nt, bool ysmem, int32_t nrows) {
   size_t fixed = nt == 32 ? solve_fixed_smem<32>() : nt == 128 ? solve_fixed_smem<128>() : solve_fixed_smem<512>();
   fixed = (fixed + 15) & ~size_t(15);
@@ -1056,6 +1548,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     });
 
     // ---- launch plan ---------------------------------------------------------------------------
+    const bool kernel_vals = m->has_val && !m->unit;
     LaunchPlan plan{};
     const double mean_col = ncols > 0 ? (double)m->nnz / ncols : 0.0;
     plan.nt = mean_col <= 128.0 ? 32 : (mean_col <= 4096.0 ? 128 : 512);
@@ -1074,17 +1567,43 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       }
     }
     plan.smem = smem_for(plan.nt, plan.ysmem, nrows);
-    int bps = 1;
     SolveArgs args{};
-    dispatch_solve(args, plan, m->has_val, s, true, &bps);
-    bps = std::max(1, bps);
-    const int max_ctas = env_int("SLIMB200_CTAS_PER_SM", bps) * m->sm_count;
-    plan.grid = std::max(1, std::min<int>(nsel, std::min(max_ctas, bps * m->sm_count)));
+    ClusterArgs cargs{};
 
-    // ---- scratch (cached on the matrix) --------------------------------------------------------
+    // yhat too large for shared memory: thread-block clusters with yhat resident in L2
+    int cs = env_int("SLIMB200_CLUSTER", plan.ysmem ? 0 : 16);
+    if (cs != 0 && cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) cs = 16;
+    const bool use_cluster = cs > 0;
     const size_t col_stride = ((size_t)std::max(ncols, 1) + 3) & ~size_t(3);
     const size_t row_stride = ((size_t)std::max(nrows, 1) + 3) & ~size_t(3);
-    const size_t g = (size_t)plan.grid;
+    int nclusters = 0;
+    if (use_cluster) {
+      int hw = kernel_vals ? cluster_launch<true>(args, cargs, cs, 1, s, true)
+                           : cluster_launch<false>(args, cargs, cs, 1, s, true);
+      if (hw < 1) throw EngineError(kErr, "learn: cluster launch configuration not supported on this device");
+      // keep the yhat vectors of all clusters in flight inside L2 (default budget 96 MB of 126 MB)
+      const size_t l2_budget = (size_t)env_int("SLIMB200_L2_MB", 96) << 20;
+      const int by_l2 = (int)std::max<size_t>(1, l2_budget / (row_stride * sizeof(double)));
+      nclusters = std::min(hw, by_l2);
+      nclusters = env_int("SLIMB200_NCLUSTERS", nclusters);
+      nclusters = std::max(1, std::min(std::min(nclusters, hw), std::max(nsel, 1)));
+      plan.grid = nclusters * cs;
+      if (env_int("SLIMB200_VERBOSE", 0))
+        fprintf(stderr, "[slim-b200] cluster kernel: cluster=%d CTAs x %d threads, %d clusters in flight (hw max %d, "
+                        "L2 budget allows %d), values=%d\n", cs, kClusterNT, nclusters, hw, by_l2, (int)kernel_vals);
+    } else {
+      int bps = 1;
+      dispatch_solve(args, plan, kernel_vals, s, true, &bps);
+      bps = std::max(1, bps);
+      const int max_ctas = env_int("SLIMB200_CTAS_PER_SM", bps) * m->sm_count;
+      plan.grid = std::max(1, std::min<int>(nsel, std::min(max_ctas, bps * m->sm_count)));
+      if (env_int("SLIMB200_VERBOSE", 0))
+        fprintf(stderr, "[slim-b200] team kernel: %d threads per target, yhat in %s, %d CTAs (%d per SM), values=%d\n",
+                plan.nt, plan.ysmem ? "smem" : "global", plan.grid, bps, (int)kernel_vals);
+    }
+
+    // ---- scratch (cached on the matrix) --------------------------------------------------------
+    const size_t g = use_cluster ? (size_t)nclusters : (size_t)plan.grid;  // scratch slots
     size_t off = 0;
     auto carve = [&](size_t bytes) {
       size_t o = off;
@@ -1093,10 +1612,10 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     };
     const size_t o_acc = carve(g * col_stride * sizeof(double));
     const size_t o_xw = carve(g * col_stride * sizeof(float));
-    const size_t o_yh = carve(plan.ysmem ? 0 : g * row_stride * sizeof(double));
+    const size_t o_yh = carve((plan.ysmem && !use_cluster) ? 0 : g * row_stride * sizeof(double));
     const size_t zero_bytes = off;  // acc, xw, yhat must start at zero
-    const size_t o_meta = carve(g * col_stride * sizeof(ActMeta));
-    const size_t o_x = carve(g * col_stride * sizeof(double));
+    const size_t o_meta = carve(g * col_stride * (use_cluster ? sizeof(ActMetaC) : sizeof(ActMeta)));
+    const size_t o_x = carve((use_cluster ? (size_t)plan.grid : g) * col_stride * sizeof(double));
     const size_t o_idx = carve(g * col_stride * sizeof(int32_t));
     if (off > m->scratch_bytes) {
       cudaFree(m->d_scratch);
@@ -1146,9 +1665,13 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     args.wncols = warm && warm->colptr ? warm->ncols : 0;
     args.acc = reinterpret_cast<double *>(sb + o_acc);
     args.xw = reinterpret_cast<float *>(sb + o_xw);
-    args.yhat = plan.ysmem ? nullptr : reinterpret_cast<double *>(sb + o_yh);
+    args.yhat = (plan.ysmem && !use_cluster) ? nullptr : reinterpret_cast<double *>(sb + o_yh);
     args.act_meta = reinterpret_cast<ActMeta *>(sb + o_meta);
     args.x = reinterpret_cast<double *>(sb + o_x);
+    cargs.colsplit = m->d_colsplit;
+    cargs.meta = reinterpret_cast<ActMetaC *>(sb + o_meta);
+    cargs.xc = reinterpret_cast<double *>(sb + o_x);
+    cargs.rows_per_part = m->rows_per_part;
     args.act_idx = reinterpret_cast<int32_t *>(sb + o_idx);
     args.col_stride = col_stride;
     args.row_stride = row_stride;
@@ -1221,7 +1744,14 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         LaunchPlan lp = plan;
         lp.grid = std::min(plan.grid, nt);
         CK(cudaEventRecord(e0, s));
-        dispatch_solve(args, lp, m->has_val, s, false, nullptr);
+        if (use_cluster) {
+          const int ncl = std::min(nclusters, nt);
+          if (kernel_vals) cluster_launch<true>(args, cargs, cs, ncl, s, false);
+          else cluster_launch<false>(args, cargs, cs, ncl, s, false);
+          CK(cudaGetLastError());
+        } else {
+          dispatch_solve(args, lp, kernel_vals, s, false, nullptr);
+        }
         CK(cudaEventRecord(e1, s));
         res->tm.launches++;
         res->tm.solve_launches++;

@@ -144,7 +144,39 @@ def test_kernel_variants_small(lib, ours, oracle, monkeypatch, nt, yglobal, rati
     ours.free(h)
 
 
-def test_long_columns_and_iteration_cap(lib, ours, oracle):
+@pytest.mark.parametrize("cs", ["1", "2", "4", "8", "16"])
+@pytest.mark.parametrize("ratings,null_vals", [(False, False), (True, False), (False, True)])
+def test_cluster_kernel_variants(lib, ours, oracle, monkeypatch, cs, ratings, null_vals):
+    # the thread-block-cluster kernel (used when yhat does not fit shared memory), forced on a small R
+    monkeypatch.setenv("SLIMB200_CLUSTER", cs)
+    rp, ri, rv = st.synth_zipf(1000, 260, 24, seed=29, ratings=ratings)
+    if null_vals:
+        rv = None
+    kw = dict(l1r=0.7, l2r=1.5, **CONV)
+    h = _learn(ours, rp, ri, rv, **kw)
+    w = oracle.learn(rp, ri, rv, nthreads=8, **kw)
+    _check_close(st.model_views(h), w)
+    ours.free(h)
+
+
+@pytest.mark.parametrize("cs", ["0", "16"])
+def test_unit_values_take_the_index_only_path(lib, ours, monkeypatch, cs):
+    # all-ones ratings: dropping the value stream on the device must not change a single bit
+    monkeypatch.setenv("SLIMB200_CLUSTER", cs)
+    rp, ri, rv = st.synth_zipf(3000, 300, 30, seed=31)
+    h0 = _learn(ours, rp, ri, rv, niters=50)
+    monkeypatch.setenv("SLIMB200_KEEP_VALUES", "1")
+    h1 = _learn(ours, rp, ri, rv, niters=50)
+    a, b = st.model_views(h0), st.model_views(h1)
+    assert np.array_equal(a["colind"], b["colind"])
+    assert np.array_equal(a["colval"].view(np.uint32), b["colval"].view(np.uint32))
+    ours.free(h0)
+    ours.free(h1)
+
+
+@pytest.mark.parametrize("cs", ["0", "8", "16"])
+def test_long_columns_and_iteration_cap(lib, ours, oracle, monkeypatch, cs):
+    monkeypatch.setenv("SLIMB200_CLUSTER", cs)
     # dense head columns (nnz ~ nusers) exercise the multi-chunk path; niters=50 caps head targets
     rp, ri, rv = st.synth_zipf(6000, 400, 40, seed=21)
     from slim_b200 import Staged, learn_columns
@@ -163,7 +195,9 @@ def test_long_columns_and_iteration_cap(lib, ours, oracle):
     assert np.allclose(stats["rnorm"], ref["stats"]["rnorm"], rtol=1e-9, atol=1e-9)
 
 
-def test_warm_start(lib, ours, oracle):
+@pytest.mark.parametrize("cs", ["0", "16"])
+def test_warm_start(lib, ours, oracle, monkeypatch, cs):
+    monkeypatch.setenv("SLIMB200_CLUSTER", cs)
     rp, ri, rv = st.synth_zipf(900, 200, 20, seed=17, ratings=True)
     h0 = _learn(ours, rp, ri, rv, l1r=3.0, l2r=1.0, niters=30)
     m0 = st.model_views(h0)
