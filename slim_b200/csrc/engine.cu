@@ -111,6 +111,7 @@ struct Matrix {
   bool has_val = false;   // the caller passed a value array
   bool unit = false;      // ... and every stored value is exactly 1.0f: the kernels then skip the value
                           // stream (4 B per nonzero instead of 8), same arithmetic as the binary path
+  double *d_wgram = nullptr;      // [ceil(ncols/32)][32][32] Gram blocks of 32 consecutive item columns
   int32_t rows_per_part = 0;      // user-range width of the 16-way column split (cluster kernel)
   int32_t *d_colsplit = nullptr;  // [ncols][kParts+1] entry offsets of the user ranges in each column
   int64_t *d_rowptr = nullptr;
@@ -146,6 +147,7 @@ void free_matrix(Matrix *m) {
   cudaFree(m->d_cnorms);
   cudaFree(m->d_csq);
   cudaFree(m->d_colsplit);
+  cudaFree(m->d_wgram);
   cudaFree(m->d_scratch);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -324,6 +326,71 @@ __global__ void column_split_kernel(int32_t ncols, int32_t rows_per_part, const 
   }
 }
 
+// Window Gram blocks.  Items are grouped into windows of 32 consecutive ids; G[w][k][m] = <a_k, a_m>
+// for the columns k, m of window w (exact: integer counts or fp64 sums of fp32 products).  With it a
+// whole window of coordinates is updated in ONE pass over its columns, exactly as sequential CD
+// would (see cd_window_kernel).  One CTA per window at a time; a user-indexed bit mask (which columns
+// of the window contain user u) finds the overlapping pairs, which are rare for sparse columns.
+template <bool HASVAL>
+__global__ void window_gram_kernel(int32_t ncols, int32_t nwin, const int64_t *__restrict__ colptr,
+                                   const int32_t *__restrict__ colcnt, const int32_t *__restrict__ colind,
+                                   const float *__restrict__ colval, uint32_t *masks, size_t mask_stride,
+                                   double *wgram) {
+  uint32_t *mask = masks + (size_t)blockIdx.x * mask_stride;
+  __shared__ double g[32][33];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int w = blockIdx.x; w < nwin; w += gridDim.x) {
+    for (int t = tid; t < 32 * 33; t += nt) (&g[0][0])[t] = 0.0;
+    const int cbase = w * 32;
+    const int nc = min(32, ncols - cbase);
+    // pass 1: set bit k of mask[u] for every entry (u) of column k
+    for (int k = 0; k < nc; k++) {
+      const int64_t c0 = colptr[cbase + k];
+      const int cnt = colcnt[cbase + k];
+      for (int e = tid; e < cnt; e += nt) atomicOr(&mask[colind[c0 + e]], 1u << k);
+    }
+    __syncthreads();
+    // pass 2: every user shared by columns k > m contributes v_ku * v_mu to G[k][m]
+    for (int k = 0; k < nc; k++) {
+      const int64_t c0 = colptr[cbase + k];
+      const int cnt = colcnt[cbase + k];
+      for (int e = tid; e < cnt; e += nt) {
+        const int u = colind[c0 + e];
+        uint32_t lower = __ldcg(&mask[u]) & ((1u << k) - 1u);  // L2: the atomics above bypass L1
+        const double vk = HASVAL ? (double)colval[c0 + e] : 1.0;
+        while (lower) {
+          const int mcol = __ffs(lower) - 1;
+          lower &= lower - 1;
+          double vm = 1.0;
+          if (HASVAL) {  // value of user u in column mcol: binary search (users ascend inside a column)
+            const int64_t m0 = colptr[cbase + mcol];
+            int lo = 0, hi = colcnt[cbase + mcol] - 1;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (colind[m0 + mid] < u) lo = mid + 1; else hi = mid;
+            }
+            vm = (double)colval[m0 + lo];
+          }
+          atomicAdd(&g[k][mcol], vk * vm);
+        }
+      }
+    }
+    __syncthreads();
+    // pass 3: clear the mask for the next window, write the (symmetric) block
+    for (int k = 0; k < nc; k++) {
+      const int64_t c0 = colptr[cbase + k];
+      const int cnt = colcnt[cbase + k];
+      for (int e = tid; e < cnt; e += nt) mask[colind[c0 + e]] = 0u;
+    }
+    double *out = wgram + (size_t)w * 1024;
+    for (int t = tid; t < 1024; t += nt) {
+      const int k = t >> 5, mcol = t & 31;
+      out[t] = k > mcol ? g[k][mcol] : (k < mcol ? g[mcol][k] : 0.0);
+    }
+    __syncthreads();
+  }
+}
+
 static int grid_for(int64_t n, int block, int sm_count) {
   int64_t g = (n + block - 1) / block;
   return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm_count * 16));
@@ -481,6 +548,24 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
       column_split_kernel<<<grid_for((int64_t)ncols * (kParts + 1), 256, m->sm_count), 256, 0, s>>>(
           ncols, m->rows_per_part, m->d_colptr, m->d_colcnt, m->d_colind, m->d_colsplit);
       m->stage_launches++;
+    }
+    if (ncols > 0) {
+      const int32_t nwin = (ncols + 31) / 32;
+      CK(cudaMalloc(&m->d_wgram, sizeof(double) * (size_t)nwin * 1024));
+      const int gw = std::max(1, std::min(nwin, m->sm_count * 2));
+      const size_t mask_stride = ((size_t)std::max(nrows, 1) + 3) & ~size_t(3);
+      DevBuf<uint32_t> d_masks;
+      d_masks.alloc_zero((size_t)gw * mask_stride, s);
+      const bool kv = m->has_val && !m->unit;
+      if (kv)
+        window_gram_kernel<true><<<gw, 512, 0, s>>>(ncols, nwin, m->d_colptr, m->d_colcnt, m->d_colind,
+                                                    m->d_colval, d_masks.p, mask_stride, m->d_wgram);
+      else
+        window_gram_kernel<false><<<gw, 512, 0, s>>>(ncols, nwin, m->d_colptr, m->d_colcnt, m->d_colind,
+                                                     nullptr, d_masks.p, mask_stride, m->d_wgram);
+      m->stage_launches++;
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(s));  // d_masks is released at scope exit
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, s));
@@ -949,11 +1034,21 @@ struct __align__(128) ActMetaC {  // one active coordinate, one 128-byte line
 };
 static_assert(sizeof(ActMetaC) == 128, "one line per active coordinate");
 
+struct GroupMeta {  // the active coordinates of one 32-item window
+  int32_t win;      // window id = item id / 32
+  uint32_t mask;    // bit b set: item win*32+b is active
+  int32_t pbase;    // position of the window's first active coordinate in the active list
+  int32_t pad;
+};
+
 struct ClusterArgs {
   const int32_t *colsplit;
   ActMetaC *meta;       // per cluster [col_stride]
   double *xc;           // per CTA [col_stride]: every CTA keeps its own copy of x (identical values)
   int32_t rows_per_part;
+  const double *wgram;  // window Gram blocks (staging)
+  GroupMeta *groups;    // per cluster [grp_stride]
+  size_t grp_stride;
 };
 
 struct CoordView {  // what one CTA needs to know about one coordinate
@@ -997,14 +1092,104 @@ __device__ __forceinline__ void axpy_chunk_r(const Chunk &r, int e0, int lo, int
 
 constexpr int kClusterNT = 512;
 
+constexpr int kSmallCol = 4096;  // entries of a column inside one CTA's user range handled by ONE warp
+
 struct ClusterSmem {
   double red[2][kClusterNT / 32];  // per-warp partials (double buffered)
   double part[2][kParts];          // per-CTA partials of the whole cluster, written through DSMEM
   int sc[kClusterNT / 32];
   int q;
   int na;
+  int ng;
   long long off;
 };
+
+struct WindowSmem {                // window sweep only
+  double G[32][32];                // Gram block of the window, G[m][k] = <a_m, a_k>
+  double pall[2][kParts][32];      // per-CTA partial inner products of every CTA (DSMEM exchange)
+  double pcta[32];                 // this CTA's partial inner product per window slot
+  double pw[kClusterNT / 32];
+  double dlt[32];                  // yhat step per window slot
+  long long c0[32];
+  int s0[32], s1[32];
+  double dl;
+};
+
+// <a, yhat> over entries [s0, s1) of a column, one warp (lanes stride the 16-byte chunks)
+template <bool HASVAL>
+__device__ __forceinline__ double warp_dot(const SolveArgs &a, int64_t c0, int s0, int s1, const double *yh) {
+  const int lane = threadIdx.x & 31;
+  double part = 0.0;
+#pragma unroll 2
+  for (int ch = (s0 >> 2) + lane; ch < ((s1 + 3) >> 2); ch += 32) {
+    Chunk c;
+    load_chunk<HASVAL>(a, c0, ch, c);
+    part += dot_chunk_r<HASVAL>(c, ch * 4, s0, s1, yh);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  return part;
+}
+
+template <bool HASVAL>
+__device__ __forceinline__ void warp_axpy(const SolveArgs &a, int64_t c0, int s0, int s1, double d, double *yh) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 2
+  for (int ch = (s0 >> 2) + lane; ch < ((s1 + 3) >> 2); ch += 32) {
+    Chunk c;
+    load_chunk<HASVAL>(a, c0, ch, c);
+    axpy_chunk_r<HASVAL>(c, ch * 4, s0, s1, d, yh);
+  }
+}
+
+// same over the whole CTA, 4 chunks in flight per thread
+template <bool HASVAL>
+__device__ __forceinline__ double block_dot(const SolveArgs &a, int64_t c0, int s0, int s1, const double *yh) {
+  constexpr int NT = kClusterNT;
+  const int ch1 = (s1 + 3) >> 2;
+  int ch = (s0 >> 2) + threadIdx.x;
+  double part = 0.0;
+  for (; ch + 3 * NT < ch1; ch += 4 * NT) {
+    Chunk c0_, c1_, c2_, c3_;
+    load_chunk<HASVAL>(a, c0, ch, c0_);
+    load_chunk<HASVAL>(a, c0, ch + NT, c1_);
+    load_chunk<HASVAL>(a, c0, ch + 2 * NT, c2_);
+    load_chunk<HASVAL>(a, c0, ch + 3 * NT, c3_);
+    part += dot_chunk_r<HASVAL>(c0_, ch * 4, s0, s1, yh);
+    part += dot_chunk_r<HASVAL>(c1_, (ch + NT) * 4, s0, s1, yh);
+    part += dot_chunk_r<HASVAL>(c2_, (ch + 2 * NT) * 4, s0, s1, yh);
+    part += dot_chunk_r<HASVAL>(c3_, (ch + 3 * NT) * 4, s0, s1, yh);
+  }
+  for (; ch < ch1; ch += NT) {
+    Chunk c;
+    load_chunk<HASVAL>(a, c0, ch, c);
+    part += dot_chunk_r<HASVAL>(c, ch * 4, s0, s1, yh);
+  }
+  return part;
+}
+
+template <bool HASVAL>
+__device__ __forceinline__ void block_axpy(const SolveArgs &a, int64_t c0, int s0, int s1, double d, double *yh) {
+  constexpr int NT = kClusterNT;
+  const int ch1 = (s1 + 3) >> 2;
+  int ch = (s0 >> 2) + threadIdx.x;
+  for (; ch + 3 * NT < ch1; ch += 4 * NT) {
+    Chunk c0_, c1_, c2_, c3_;
+    load_chunk<HASVAL>(a, c0, ch, c0_);
+    load_chunk<HASVAL>(a, c0, ch + NT, c1_);
+    load_chunk<HASVAL>(a, c0, ch + 2 * NT, c2_);
+    load_chunk<HASVAL>(a, c0, ch + 3 * NT, c3_);
+    axpy_chunk_r<HASVAL>(c0_, ch * 4, s0, s1, d, yh);
+    axpy_chunk_r<HASVAL>(c1_, (ch + NT) * 4, s0, s1, d, yh);
+    axpy_chunk_r<HASVAL>(c2_, (ch + 2 * NT) * 4, s0, s1, d, yh);
+    axpy_chunk_r<HASVAL>(c3_, (ch + 3 * NT) * 4, s0, s1, d, yh);
+  }
+  for (; ch < ch1; ch += NT) {
+    Chunk c;
+    load_chunk<HASVAL>(a, c0, ch, c);
+    axpy_chunk_r<HASVAL>(c, ch * 4, s0, s1, d, yh);
+  }
+}
 
 // Sum over all threads of the cluster; every thread of every CTA returns the bit-identical value.
 __device__ __forceinline__ double cluster_sum(double v, ClusterSmem &sm, int &par, cg::cluster_group &cl,
@@ -1028,10 +1213,11 @@ __device__ __forceinline__ double cluster_sum(double v, ClusterSmem &sm, int &pa
   return tot;
 }
 
-template <bool HASVAL>
+template <bool HASVAL, bool WINDOW>
 __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveArgs a, const ClusterArgs ca) {
   constexpr int NT = kClusterNT, NW = NT / 32;
   __shared__ ClusterSmem sm;
+  __shared__ WindowSmem ws;
   cg::cluster_group cl = cg::this_cluster();
   const int cs = (int)cl.num_blocks();
   const int rank = (int)cl.block_rank();
@@ -1047,6 +1233,7 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
   float *xw = a.xw + (size_t)cid * a.col_stride;
   int32_t *act_idx = a.act_idx + (size_t)cid * a.col_stride;
   ActMetaC *meta = ca.meta + (size_t)cid * a.col_stride;
+  GroupMeta *groups = ca.groups + (size_t)cid * ca.grp_stride;
   double *x = ca.xc + (size_t)blockIdx.x * a.col_stride;
   double *yh = a.yhat + (size_t)cid * a.row_stride;
 
@@ -1089,7 +1276,7 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
     // ---- active set, built by CTA 0, read by all ----------------------------------------------------
     long long actnnz = 0;
     if (rank == 0) {
-      int na = 0;
+      int na = 0, ng = 0;
       for (int base = 0; base < a.ncols; base += NT) {
         const int i = base + tid;
         double v = 0.0;
@@ -1117,10 +1304,30 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
           act_idx[pos] = i;
           actnnz += m.cnt;
         }
+        if (WINDOW) {
+          // a warp covers exactly one 32-item window (base is a multiple of 512): its ballot is the
+          // window's active mask, and lane 0's scan value is the position of its first active coordinate
+          const unsigned wmask = __ballot_sync(0xffffffffu, flag);
+          const bool gflag = (lane == 0) && (wmask != 0u);
+          int gtot;
+          const int gpos = ng + team_excl_scan<NT>(gflag, sm.sc, gtot);
+          if (gflag) {
+            GroupMeta gm;
+            gm.win = (base >> 5) + warp;
+            gm.mask = wmask;
+            gm.pbase = pos;
+            gm.pad = 0;
+            groups[gpos] = gm;
+          }
+          ng += gtot;
+        }
         na += tot;
       }
       if (tid == 0)
-        for (int c = 0; c < cs; c++) *cl.map_shared_rank(&sm.na, c) = na;
+        for (int c = 0; c < cs; c++) {
+          *cl.map_shared_rank(&sm.na, c) = na;
+          *cl.map_shared_rank(&sm.ng, c) = ng;
+        }
     }
     __threadfence();
     cl.sync();
@@ -1158,7 +1365,137 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
 
     // ---- K2: sweeps ---------------------------------------------------------------------------------
     int niters = 1;
-    if (na > 0 && maxit > 0) {
+    if (WINDOW && na > 0 && maxit > 0) {
+      // Exact block form of sequential CD.  For the active coordinates k of one 32-item window, taken
+      // in ascending order, sequential CD needs ip_k = <a_k, yhat> AFTER the steps of the earlier
+      // coordinates m < k of the window:  <a_k, yhat_0> + sum_{m<k} d_m <a_k, a_m>.  The first term comes
+      // from ONE pass over the window's columns against the yhat at the start of the round, the second
+      // from the precomputed Gram block, so a round costs one cluster barrier for up to 32 coordinates.
+      const int ng = sm.ng;
+      bool done = false;
+      int t = 0;
+      for (; t < maxit && !done; t++) {
+        double dltx = 0.0;
+        for (int g = 0; g < ng; g++) {
+          const int4 gm = __ldcg(reinterpret_cast<const int4 *>(groups + g));
+          const int win = gm.x;
+          const unsigned mask = (unsigned)gm.y;
+          const int pbase = gm.z;
+          float r_aty = 0.f;
+          double r_den = 1.0, r_sq = 0.0;
+          int r_p = 0;
+          if (tid < 32) {
+            if ((mask >> tid) & 1u) {
+              r_p = pbase + __popc(mask & ((1u << tid) - 1u));
+              const CoordView v = load_view(&meta[r_p], pr0, pr1);
+              ws.c0[tid] = v.c0;
+              ws.s0[tid] = v.s0;
+              ws.s1[tid] = v.s1;
+              r_aty = v.aty;
+              r_den = v.den;
+              r_sq = v.sq;
+            }
+            ws.pcta[tid] = 0.0;
+          }
+          reinterpret_cast<double2 *>(&ws.G[0][0])[tid] =
+              __ldg(reinterpret_cast<const double2 *>(ca.wgram + (size_t)win * 1024) + tid);
+          __syncthreads();
+
+          // gather: small columns one warp each, large columns by the whole CTA
+          {
+            int ord = 0;
+            for (unsigned mm = mask; mm; mm &= mm - 1) {
+              const int b = __ffs(mm) - 1;
+              const int s0 = ws.s0[b], s1 = ws.s1[b];
+              if (s1 - s0 <= kSmallCol) {
+                if ((ord & (NW - 1)) == warp) {
+                  const double v = warp_dot<HASVAL>(a, ws.c0[b], s0, s1, yh);
+                  if (lane == 0) ws.pcta[b] = v;
+                }
+                ord++;
+              }
+            }
+            for (unsigned mm = mask; mm; mm &= mm - 1) {
+              const int b = __ffs(mm) - 1;
+              const int s0 = ws.s0[b], s1 = ws.s1[b];
+              if (s1 - s0 > kSmallCol) {
+                double v = block_dot<HASVAL>(a, ws.c0[b], s0, s1, yh);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) ws.pw[warp] = v;
+                __syncthreads();
+                if (tid == 0) {
+                  double sum = 0.0;
+#pragma unroll
+                  for (int i = 0; i < NW; i++) sum += ws.pw[i];
+                  ws.pcta[b] = sum;
+                }
+                __syncthreads();
+              }
+            }
+          }
+          __syncthreads();
+          {
+            const int dst = tid >> 5, b = tid & 31;
+            if (dst < cs) *cl.map_shared_rank(&ws.pall[par][rank][b], dst) = ws.pcta[b];
+          }
+          cl.sync();
+
+          // Gram-space sequential solve of the window by warp 0 (identical in every CTA)
+          if (warp == 0) {
+            const bool act = (mask >> lane) & 1u;
+            double P = 0.0;
+            if (act)
+              for (int c = 0; c < cs; c++) P += ws.pall[par][c][lane];
+            const double xi = act ? x[r_p] : 0.0;
+            const double in_old = fabs(xi) > kEps ? xi : 0.0;
+            double ip = P - in_old * r_sq;
+            double nx = xi, d = 0.0;
+            for (unsigned mm = mask; mm; mm &= mm - 1) {
+              const int mb = __ffs(mm) - 1;
+              double dm = 0.0;
+              if (lane == mb) {
+                const double num = (double)r_aty - ip;
+                nx = num > a.l1r ? (num - a.l1r) / r_den : 0.0;
+                const double in_new = fabs(nx) > kEps ? nx : 0.0;
+                d = in_new - in_old;
+                dm = d;
+              }
+              dm = __shfl_sync(0xffffffffu, dm, mb);
+              if (dm != 0.0 && act && lane > mb) ip += dm * ws.G[mb][lane];
+            }
+            if (act) x[r_p] = nx;
+            ws.dlt[lane] = act ? d : 0.0;
+            double dd = act ? (nx - xi) * (nx - xi) : 0.0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+            if (lane == 0) ws.dl = dd;
+          }
+          __syncthreads();
+          dltx += ws.dl;
+
+          // update this CTA's yhat slice: yhat += sum_k d_k a_k
+          {
+            int ord = 0;
+            for (unsigned mm = mask; mm; mm &= mm - 1) {
+              const int b = __ffs(mm) - 1;
+              const int s0 = ws.s0[b], s1 = ws.s1[b];
+              const double d = ws.dlt[b];
+              if (s1 - s0 <= kSmallCol) {
+                if ((ord & (NW - 1)) == warp && d != 0.0) warp_axpy<HASVAL>(a, ws.c0[b], s0, s1, d, yh);
+                ord++;
+              } else if (d != 0.0) {
+                block_axpy<HASVAL>(a, ws.c0[b], s0, s1, d, yh);
+              }
+            }
+          }
+          __syncthreads();
+          par ^= 1;
+        }
+        if (dltx < a.opttol) done = true;
+      }
+      niters = done ? t : maxit + 1;
+    } else if (na > 0 && maxit > 0) {
       CoordView v_cur = load_view(&meta[0], pr0, pr1);
       CoordView v_nxt = load_view(&meta[na > 1 ? 1 : 0], pr0, pr1);
       Chunk c_cur;
@@ -1478,10 +1815,10 @@ static void dispatch_solve(const SolveArgs &args, const LaunchPlan &plan, bool h
   throw EngineError(kErr, "dispatch_solve: unsupported team size");
 }
 
-template <bool HASVAL>
+template <bool HASVAL, bool WINDOW>
 static int cluster_launch(const SolveArgs &args, const ClusterArgs &cargs, int cs, int nclusters, cudaStream_t s,
                           bool query_only) {
-  auto kern = cd_cluster_kernel<HASVAL>;
+  auto kern = cd_cluster_kernel<HASVAL, WINDOW>;
   if (cs > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
@@ -1502,6 +1839,16 @@ static int cluster_launch(const SolveArgs &args, const ClusterArgs &cargs, int c
   }
   CK(cudaLaunchKernelEx(&cfg, kern, args, cargs));
   return 0;
+}
+
+static int cluster_dispatch(bool vals, bool window, const SolveArgs &args, const ClusterArgs &cargs, int cs,
+                            int nclusters, cudaStream_t s, bool query_only) {
+  if (vals) {
+    return window ? cluster_launch<true, true>(args, cargs, cs, nclusters, s, query_only)
+                  : cluster_launch<true, false>(args, cargs, cs, nclusters, s, query_only);
+  }
+  return window ? cluster_launch<false, true>(args, cargs, cs, nclusters, s, query_only)
+                : cluster_launch<false, false>(args, cargs, cs, nclusters, s, query_only);
 }
 
 static size_t smem_for(int nt, bool ysmem, int32_t nrows) {
@@ -1574,23 +1921,24 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     int cs = env_int("SLIMB200_CLUSTER", plan.ysmem ? 0 : 16);
     if (cs != 0 && cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) cs = 16;
     const bool use_cluster = cs > 0;
+    const bool use_window = use_cluster && env_int("SLIMB200_WINDOW", 1) != 0;
     const size_t col_stride = ((size_t)std::max(ncols, 1) + 3) & ~size_t(3);
     const size_t row_stride = ((size_t)std::max(nrows, 1) + 3) & ~size_t(3);
     int nclusters = 0;
     if (use_cluster) {
-      int hw = kernel_vals ? cluster_launch<true>(args, cargs, cs, 1, s, true)
-                           : cluster_launch<false>(args, cargs, cs, 1, s, true);
+      int hw = cluster_dispatch(kernel_vals, use_window, args, cargs, cs, 1, s, true);
       if (hw < 1) throw EngineError(kErr, "learn: cluster launch configuration not supported on this device");
       // keep the yhat vectors of all clusters in flight inside L2 (default budget 96 MB of 126 MB)
       const size_t l2_budget = (size_t)env_int("SLIMB200_L2_MB", 96) << 20;
       const int by_l2 = (int)std::max<size_t>(1, l2_budget / (row_stride * sizeof(double)));
       nclusters = std::min(hw, by_l2);
-      nclusters = env_int("SLIMB200_NCLUSTERS", nclusters);
+      if (env_int("SLIMB200_NCLUSTERS", 0) > 0) nclusters = env_int("SLIMB200_NCLUSTERS", 0);
       nclusters = std::max(1, std::min(std::min(nclusters, hw), std::max(nsel, 1)));
       plan.grid = nclusters * cs;
       if (env_int("SLIMB200_VERBOSE", 0))
         fprintf(stderr, "[slim-b200] cluster kernel: cluster=%d CTAs x %d threads, %d clusters in flight (hw max %d, "
-                        "L2 budget allows %d), values=%d\n", cs, kClusterNT, nclusters, hw, by_l2, (int)kernel_vals);
+                        "L2 budget allows %d), values=%d, window sweep=%d\n", cs, kClusterNT, nclusters, hw, by_l2,
+                (int)kernel_vals, (int)use_window);
     } else {
       int bps = 1;
       dispatch_solve(args, plan, kernel_vals, s, true, &bps);
@@ -1617,6 +1965,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     const size_t o_meta = carve(g * col_stride * (use_cluster ? sizeof(ActMetaC) : sizeof(ActMeta)));
     const size_t o_x = carve((use_cluster ? (size_t)plan.grid : g) * col_stride * sizeof(double));
     const size_t o_idx = carve(g * col_stride * sizeof(int32_t));
+    const size_t grp_stride = (size_t)(ncols + 31) / 32 + 1;
+    const size_t o_grp = carve(use_cluster ? g * grp_stride * sizeof(GroupMeta) : 0);
     if (off > m->scratch_bytes) {
       cudaFree(m->d_scratch);
       m->d_scratch = nullptr;
@@ -1672,6 +2022,9 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     cargs.meta = reinterpret_cast<ActMetaC *>(sb + o_meta);
     cargs.xc = reinterpret_cast<double *>(sb + o_x);
     cargs.rows_per_part = m->rows_per_part;
+    cargs.wgram = m->d_wgram;
+    cargs.groups = reinterpret_cast<GroupMeta *>(sb + o_grp);
+    cargs.grp_stride = grp_stride;
     args.act_idx = reinterpret_cast<int32_t *>(sb + o_idx);
     args.col_stride = col_stride;
     args.row_stride = row_stride;
@@ -1746,8 +2099,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         CK(cudaEventRecord(e0, s));
         if (use_cluster) {
           const int ncl = std::min(nclusters, nt);
-          if (kernel_vals) cluster_launch<true>(args, cargs, cs, ncl, s, false);
-          else cluster_launch<false>(args, cargs, cs, ncl, s, false);
+          cluster_dispatch(kernel_vals, use_window, args, cargs, cs, ncl, s, false);
           CK(cudaGetLastError());
         } else {
           dispatch_solve(args, lp, kernel_vals, s, false, nullptr);

@@ -145,10 +145,14 @@ def test_kernel_variants_small(lib, ours, oracle, monkeypatch, nt, yglobal, rati
 
 
 @pytest.mark.parametrize("cs", ["1", "2", "4", "8", "16"])
+@pytest.mark.parametrize("window", ["0", "1"])
 @pytest.mark.parametrize("ratings,null_vals", [(False, False), (True, False), (False, True)])
-def test_cluster_kernel_variants(lib, ours, oracle, monkeypatch, cs, ratings, null_vals):
-    # the thread-block-cluster kernel (used when yhat does not fit shared memory), forced on a small R
+def test_cluster_kernel_variants(lib, ours, oracle, monkeypatch, cs, window, ratings, null_vals):
+    # the thread-block-cluster kernel (used when yhat does not fit shared memory), forced on a small R;
+    # window=1: 32-coordinate exact block updates through the staged Gram blocks, window=0: one
+    # coordinate per cluster barrier
     monkeypatch.setenv("SLIMB200_CLUSTER", cs)
+    monkeypatch.setenv("SLIMB200_WINDOW", window)
     rp, ri, rv = st.synth_zipf(1000, 260, 24, seed=29, ratings=ratings)
     if null_vals:
         rv = None
@@ -174,9 +178,10 @@ def test_unit_values_take_the_index_only_path(lib, ours, monkeypatch, cs):
     ours.free(h1)
 
 
-@pytest.mark.parametrize("cs", ["0", "8", "16"])
-def test_long_columns_and_iteration_cap(lib, ours, oracle, monkeypatch, cs):
+@pytest.mark.parametrize("cs,window", [("0", "1"), ("8", "0"), ("8", "1"), ("16", "1"), ("2", "1")])
+def test_long_columns_and_iteration_cap(lib, ours, oracle, monkeypatch, cs, window):
     monkeypatch.setenv("SLIMB200_CLUSTER", cs)
+    monkeypatch.setenv("SLIMB200_WINDOW", window)
     # dense head columns (nnz ~ nusers) exercise the multi-chunk path; niters=50 caps head targets
     rp, ri, rv = st.synth_zipf(6000, 400, 40, seed=21)
     from slim_b200 import Staged, learn_columns
@@ -211,6 +216,25 @@ def test_warm_start(lib, ours, oracle, monkeypatch, cs):
     assert maxd > 1e-4
     for h in (h0, h1, hc):
         ours.free(h)
+
+
+def test_window_sweep_large_and_small_columns(lib, ours, oracle, monkeypatch):
+    # 40K users: head columns exceed the one-warp threshold (4096 entries per CTA range) with small
+    # clusters, tail columns stay below it -- both gather paths of the window sweep in one window
+    from slim_b200 import Staged, learn_columns
+
+    rp, ri, rv = st.synth_zipf(40000, 600, 30, seed=77)
+    cols = np.arange(0, 600, 13, dtype=np.int32)
+    ref = oracle.learn(rp, ri, rv, niters=30, cols=cols, nthreads=8, want_stats=True)
+    for cs in ("1", "4", "16"):
+        monkeypatch.setenv("SLIMB200_CLUSTER", cs)
+        with Staged(rp, ri, rv) as s:
+            r = learn_columns(s, dict(niters=30), cols=cols)
+            got, stats = r.to_host(), r.stats()
+        assert np.array_equal(stats["niters"], ref["stats"]["niters"])
+        assert np.array_equal(stats["nactive"], ref["stats"]["nactive"])
+        _check_close(got, ref, tol=1e-6)
+        assert np.allclose(stats["objval"], ref["stats"]["objval"], rtol=1e-9)
 
 
 def test_edge_cases(lib, ours, oracle):
