@@ -1104,7 +1104,7 @@ struct ClusterSmem {
   long long off;
 };
 
-struct WindowSmem {                // window sweep only
+struct __align__(16) WindowSmem {  // window sweep only
   double G[32][32];                // Gram block of the window, G[m][k] = <a_m, a_k>
   double pall[2][kParts][32];      // per-CTA partial inner products of every CTA (DSMEM exchange)
   double pcta[32];                 // this CTA's partial inner product per window slot
