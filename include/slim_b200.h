@@ -42,6 +42,10 @@ int32_t SLIMB200_MatrixInfo(const slimb200_matrix_t *matrix, int32_t *nrows, int
 int32_t SLIMB200_MatrixCSC(const slimb200_matrix_t *matrix, int64_t *colptr, int32_t *colind,
                            float *colval, float *cnorms);
 
+/* Copy the staged window Gram blocks back (tests): double[ceil(ncols/32)][32][32], block w holds
+ * <a_k, a_m> for the item columns 32w+k and 32w+m (zero diagonal). */
+int32_t SLIMB200_MatrixWindowGram(const slimb200_matrix_t *matrix, double *out);
+
 /* Solve target columns cols[0..ncols_sel) (cols == NULL: every column): the per-column body of
  * EstimateModelCD (reference src/libslim/estimate.c:405-505) + CoordinateDescent (cd.c:101-142).
  * Options as for SLIM_Learn.  imodel: optional warm-start model handle. */

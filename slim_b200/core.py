@@ -333,6 +333,13 @@ class Staged:
         assert rc == SLIM_OK
         return dict(colptr=cp, colind=ci[:self.nnz], colval=cv[:self.nnz], cnorms=cn[:self.ncols])
 
+    def window_gram(self):
+        nwin = (self.ncols + 31) // 32
+        out = np.zeros((max(nwin, 1), 32, 32), np.float64)
+        rc = self._lib.SLIMB200_MatrixWindowGram(self.handle, _ptr(out, C.c_double))
+        assert rc == SLIM_OK
+        return out[:nwin]
+
     def close(self):
         if getattr(self, "handle", None):
             h = C.c_void_p(self.handle)

@@ -736,6 +736,11 @@ int32_t SLIMB200_MatrixCSC(const slimb200_matrix_t *matrix, int64_t *colptr, int
   return matrix_csc_to_host(reinterpret_cast<const Matrix *>(matrix), colptr, colind, colval, cnorms);
 }
 
+int32_t SLIMB200_MatrixWindowGram(const slimb200_matrix_t *matrix, double *out) {
+  if (!matrix) return SLIM_ERROR_INPUT;
+  return matrix_window_gram_to_host(reinterpret_cast<const Matrix *>(matrix), out);
+}
+
 slimb200_result_t *SLIMB200_LearnColumns(slimb200_matrix_t *matrix, const int32_t *ioptions, const double *doptions,
                                          const int32_t *cols, int32_t ncols_sel, const slim_t *imodel,
                                          int32_t *r_status) {

@@ -588,6 +588,18 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
   return nullptr;
 }
 
+int matrix_window_gram_to_host(const Matrix *m, double *out) {
+  try {
+    DeviceGuard guard(m->device);
+    const size_t n = (size_t)((m->ncols + 31) / 32) * 1024;
+    if (n > 0) CK(cudaMemcpy(out, m->d_wgram, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return kOk;
+  } catch (const EngineError &e) {
+    g_last_error = e.what();
+    return e.status;
+  }
+}
+
 int matrix_csc_to_host(const Matrix *m, int64_t *colptr, int32_t *colind, float *colval,
                        float *cnorms) {
   try {
@@ -1072,22 +1084,34 @@ __device__ __forceinline__ CoordView load_view(const ActMetaC *m, int pr0, int p
   return v;
 }
 
-template <bool HASVAL>
+// L2 = true: yhat is read with ld.global.cg and updated with fp64 atomics.  The window sweep needs
+// this because several warps update DIFFERENT columns of a window at the same time and those columns
+// can share users (inside one column the users are distinct, so the one-column-at-a-time paths can use
+// plain loads and stores).
+template <bool HASVAL, bool L2 = false>
 __device__ __forceinline__ double dot_chunk_r(const Chunk &r, int e0, int lo, int hi, const double *yh) {
   double s = 0.0;
-  if (e0 + 0 >= lo && e0 + 0 < hi) s += HASVAL ? (double)r.vv.x * yh[r.ix.x] : yh[r.ix.x];
-  if (e0 + 1 >= lo && e0 + 1 < hi) s += HASVAL ? (double)r.vv.y * yh[r.ix.y] : yh[r.ix.y];
-  if (e0 + 2 >= lo && e0 + 2 < hi) s += HASVAL ? (double)r.vv.z * yh[r.ix.z] : yh[r.ix.z];
-  if (e0 + 3 >= lo && e0 + 3 < hi) s += HASVAL ? (double)r.vv.w * yh[r.ix.w] : yh[r.ix.w];
+#define SLIM_YH(i) (L2 ? __ldcg(yh + (i)) : yh[(i)])
+  if (e0 + 0 >= lo && e0 + 0 < hi) s += HASVAL ? (double)r.vv.x * SLIM_YH(r.ix.x) : SLIM_YH(r.ix.x);
+  if (e0 + 1 >= lo && e0 + 1 < hi) s += HASVAL ? (double)r.vv.y * SLIM_YH(r.ix.y) : SLIM_YH(r.ix.y);
+  if (e0 + 2 >= lo && e0 + 2 < hi) s += HASVAL ? (double)r.vv.z * SLIM_YH(r.ix.z) : SLIM_YH(r.ix.z);
+  if (e0 + 3 >= lo && e0 + 3 < hi) s += HASVAL ? (double)r.vv.w * SLIM_YH(r.ix.w) : SLIM_YH(r.ix.w);
+#undef SLIM_YH
   return s;
 }
 
-template <bool HASVAL>
+template <bool HASVAL, bool L2 = false>
 __device__ __forceinline__ void axpy_chunk_r(const Chunk &r, int e0, int lo, int hi, double d, double *yh) {
-  if (e0 + 0 >= lo && e0 + 0 < hi) yh[r.ix.x] += HASVAL ? d * (double)r.vv.x : d;
-  if (e0 + 1 >= lo && e0 + 1 < hi) yh[r.ix.y] += HASVAL ? d * (double)r.vv.y : d;
-  if (e0 + 2 >= lo && e0 + 2 < hi) yh[r.ix.z] += HASVAL ? d * (double)r.vv.z : d;
-  if (e0 + 3 >= lo && e0 + 3 < hi) yh[r.ix.w] += HASVAL ? d * (double)r.vv.w : d;
+#define SLIM_UPD(i, v)                   \
+  do {                                   \
+    if (L2) atomicAdd(yh + (i), (v));    \
+    else yh[(i)] += (v);                 \
+  } while (0)
+  if (e0 + 0 >= lo && e0 + 0 < hi) SLIM_UPD(r.ix.x, HASVAL ? d * (double)r.vv.x : d);
+  if (e0 + 1 >= lo && e0 + 1 < hi) SLIM_UPD(r.ix.y, HASVAL ? d * (double)r.vv.y : d);
+  if (e0 + 2 >= lo && e0 + 2 < hi) SLIM_UPD(r.ix.z, HASVAL ? d * (double)r.vv.z : d);
+  if (e0 + 3 >= lo && e0 + 3 < hi) SLIM_UPD(r.ix.w, HASVAL ? d * (double)r.vv.w : d);
+#undef SLIM_UPD
 }
 
 constexpr int kClusterNT = 512;
@@ -1124,7 +1148,7 @@ __device__ __forceinline__ double warp_dot(const SolveArgs &a, int64_t c0, int s
   for (int ch = (s0 >> 2) + lane; ch < ((s1 + 3) >> 2); ch += 32) {
     Chunk c;
     load_chunk<HASVAL>(a, c0, ch, c);
-    part += dot_chunk_r<HASVAL>(c, ch * 4, s0, s1, yh);
+    part += dot_chunk_r<HASVAL, true>(c, ch * 4, s0, s1, yh);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -1138,7 +1162,7 @@ __device__ __forceinline__ void warp_axpy(const SolveArgs &a, int64_t c0, int s0
   for (int ch = (s0 >> 2) + lane; ch < ((s1 + 3) >> 2); ch += 32) {
     Chunk c;
     load_chunk<HASVAL>(a, c0, ch, c);
-    axpy_chunk_r<HASVAL>(c, ch * 4, s0, s1, d, yh);
+    axpy_chunk_r<HASVAL, true>(c, ch * 4, s0, s1, d, yh);
   }
 }
 
@@ -1155,15 +1179,15 @@ __device__ __forceinline__ double block_dot(const SolveArgs &a, int64_t c0, int 
     load_chunk<HASVAL>(a, c0, ch + NT, c1_);
     load_chunk<HASVAL>(a, c0, ch + 2 * NT, c2_);
     load_chunk<HASVAL>(a, c0, ch + 3 * NT, c3_);
-    part += dot_chunk_r<HASVAL>(c0_, ch * 4, s0, s1, yh);
-    part += dot_chunk_r<HASVAL>(c1_, (ch + NT) * 4, s0, s1, yh);
-    part += dot_chunk_r<HASVAL>(c2_, (ch + 2 * NT) * 4, s0, s1, yh);
-    part += dot_chunk_r<HASVAL>(c3_, (ch + 3 * NT) * 4, s0, s1, yh);
+    part += dot_chunk_r<HASVAL, true>(c0_, ch * 4, s0, s1, yh);
+    part += dot_chunk_r<HASVAL, true>(c1_, (ch + NT) * 4, s0, s1, yh);
+    part += dot_chunk_r<HASVAL, true>(c2_, (ch + 2 * NT) * 4, s0, s1, yh);
+    part += dot_chunk_r<HASVAL, true>(c3_, (ch + 3 * NT) * 4, s0, s1, yh);
   }
   for (; ch < ch1; ch += NT) {
     Chunk c;
     load_chunk<HASVAL>(a, c0, ch, c);
-    part += dot_chunk_r<HASVAL>(c, ch * 4, s0, s1, yh);
+    part += dot_chunk_r<HASVAL, true>(c, ch * 4, s0, s1, yh);
   }
   return part;
 }
@@ -1179,15 +1203,15 @@ __device__ __forceinline__ void block_axpy(const SolveArgs &a, int64_t c0, int s
     load_chunk<HASVAL>(a, c0, ch + NT, c1_);
     load_chunk<HASVAL>(a, c0, ch + 2 * NT, c2_);
     load_chunk<HASVAL>(a, c0, ch + 3 * NT, c3_);
-    axpy_chunk_r<HASVAL>(c0_, ch * 4, s0, s1, d, yh);
-    axpy_chunk_r<HASVAL>(c1_, (ch + NT) * 4, s0, s1, d, yh);
-    axpy_chunk_r<HASVAL>(c2_, (ch + 2 * NT) * 4, s0, s1, d, yh);
-    axpy_chunk_r<HASVAL>(c3_, (ch + 3 * NT) * 4, s0, s1, d, yh);
+    axpy_chunk_r<HASVAL, true>(c0_, ch * 4, s0, s1, d, yh);
+    axpy_chunk_r<HASVAL, true>(c1_, (ch + NT) * 4, s0, s1, d, yh);
+    axpy_chunk_r<HASVAL, true>(c2_, (ch + 2 * NT) * 4, s0, s1, d, yh);
+    axpy_chunk_r<HASVAL, true>(c3_, (ch + 3 * NT) * 4, s0, s1, d, yh);
   }
   for (; ch < ch1; ch += NT) {
     Chunk c;
     load_chunk<HASVAL>(a, c0, ch, c);
-    axpy_chunk_r<HASVAL>(c, ch * 4, s0, s1, d, yh);
+    axpy_chunk_r<HASVAL, true>(c, ch * 4, s0, s1, d, yh);
   }
 }
 
@@ -1599,13 +1623,13 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
         const int u = a.colind[cj0 + e];
         const double v = HASVAL ? (double)a.colval[cj0 + e] : 1.0;
         yy += v * v;
-        yd += v * yh[u];
+        yd += v * __ldcg(&yh[u]);
       }
     }
     __syncthreads();
     double hh = 0.0;
     for (int u = u_lo + tid; u < u_hi; u += NT) {
-      const double h = yh[u];
+      const double h = __ldcg(&yh[u]);
       if (h != 0.0) {
         hh += h * h;
         yh[u] = 0.0;

@@ -46,6 +46,9 @@ void matrix_info(const Matrix *m, int32_t *nrows, int32_t *ncols, int64_t *nnz, 
 int matrix_csc_to_host(const Matrix *m, int64_t *colptr, int32_t *colind, float *colval,
                        float *cnorms);
 
+// Window Gram blocks (tests): double[ceil(ncols/32)][32][32].
+int matrix_window_gram_to_host(const Matrix *m, double *out);
+
 Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel,
               const WarmStart *warm, int32_t *status);
 void free_result(Result *r);

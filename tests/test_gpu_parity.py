@@ -86,6 +86,27 @@ def test_staging_float_norm_rounding(lib, oracle):
     assert np.array_equal(got["cnorms"].view(np.uint32), ref["cnorms"].view(np.uint32))
 
 
+@pytest.mark.parametrize("ratings", [False, True])
+def test_window_gram_blocks(lib, ratings):
+    # staged Gram blocks of 32 consecutive item columns == the diagonal blocks of R^T R (exact)
+    import scipy.sparse as sp
+
+    from slim_b200 import Staged
+
+    rp, ri, rv = st.synth_zipf(3000, 200, 25, seed=8, ratings=ratings)
+    R = sp.csr_matrix((rv.astype(np.float64), ri, rp), shape=(3000, 200))
+    G = (R.T @ R).toarray()
+    with Staged(rp, ri, rv) as s:
+        got = s.window_gram()
+    assert got.shape == (7, 32, 32)
+    for w in range(7):
+        n = min(32, 200 - 32 * w)
+        ref = G[32 * w:32 * w + n, 32 * w:32 * w + n].copy()
+        np.fill_diagonal(ref, 0.0)
+        assert np.array_equal(got[w, :n, :n], ref), w
+        assert not got[w, n:, :].any() and not got[w, :, n:].any()
+
+
 @pytest.mark.parametrize("name", ["ml100k", "automotive"])
 def test_learn_matches_reference_golden(lib, ours, name):
     g = st.load_golden(name)
