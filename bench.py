@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument("--l1r", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dump-targets", default=None,
+                    help="write per-target counters of the timed steps (csv) to this file")
     return ap.parse_args()
 
 
@@ -285,7 +287,7 @@ def main():
             res.to_device(counts, ind, val)
             all_gather_columns(mine, counts[:res.nsel], ind[:res.nnz], val[:res.nnz], len(cols))
         if keep is not None:
-            keep.append((cols[mine], res.stats(), res.nnz, res.solve_ms, res.launches))
+            keep.append((cols[mine], res.stats(), res.nnz, res.solve_ms, res.launches, res.phases()))
         res.close()
 
     for s in range(args.warmup):
@@ -315,7 +317,17 @@ def main():
     solve_ms = 0.0
     launches = 0
     sweeps_all = []
-    for cols, stats, wnnz, sms, nl in kept:
+    if args.dump_targets and rank == 0:
+        with open(args.dump_targets, "w") as f:
+            f.write("col,c_j,nactive,rounds_per_sweep,niters,active_nnz,us_candidates,us_active_set,us_sweeps,"
+                    "us_epilogue,us_per_round\n")
+            for cols, stats, wnnz, sms, nl, (ph, ng) in kept:
+                for k in np.argsort(-ph[:, 2]):
+                    rounds = max(int(ng[k]) * max(int(min(stats["niters"][k], PARAMS["niters"])), 1), 1)
+                    f.write(f"{cols[k]},{colcnt[cols[k]]},{stats['nactive'][k]},{ng[k]},{stats['niters'][k]},"
+                            f"{stats['active_nnz'][k]},{ph[k,0]:.0f},{ph[k,1]:.0f},{ph[k,2]:.0f},{ph[k,3]:.0f},"
+                            f"{ph[k,2] / rounds:.2f}\n")
+    for cols, stats, wnnz, sms, nl, _ph in kept:
         cb, sb, ob, sw = algorithmic_bytes(colcnt, cols, stats, wnnz, PARAMS["niters"])
         cand_b, sweep_b, out_b = cand_b + cb, sweep_b + sb, out_b + ob
         solve_ms += sms

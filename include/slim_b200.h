@@ -62,6 +62,10 @@ int32_t SLIMB200_ResultInfo(const slimb200_result_t *result, int32_t *nsel, int6
  * 1/2||y - yhat||^2 and the objective (estimate.c:477-489). */
 int32_t SLIMB200_ResultStats(const slimb200_result_t *result, int32_t *niters, int32_t *nactive,
                              int64_t *active_nnz, int64_t *expand_nnz, double *rnorm, double *objval);
+/* Profiling counters of the cluster kernel per column: phase_us float[nsel][4] = microseconds spent in
+ * candidate expansion, active-set build, sweeps, epilogue; rounds int32[nsel] = barrier rounds per sweep.
+ * Zeros when the single-CTA kernel was used. */
+int32_t SLIMB200_ResultPhases(const slimb200_result_t *result, float *phase_us, int32_t *rounds);
 /* Solved columns as CSC: colptr int64[nsel+1], colind int32[nnz] (ascending), colval float[nnz]. */
 int32_t SLIMB200_ResultToHost(const slimb200_result_t *result, int64_t *colptr, int32_t *colind,
                               float *colval);

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "SLIMB200_FreeResult": (None, [C.POINTER(C.c_void_p)]),
     "SLIMB200_ResultInfo": (C.c_int32, [C.c_void_p, c_i32p, c_i64p, c_f64p, c_f64p, c_i32p]),
     "SLIMB200_ResultStats": (C.c_int32, [C.c_void_p, c_i32p, c_i32p, c_i64p, c_i64p, c_f64p, c_f64p]),
+    "SLIMB200_ResultPhases": (C.c_int32, [C.c_void_p, c_f32p, c_i32p]),
     "SLIMB200_ResultToHost": (C.c_int32, [C.c_void_p, c_i64p, c_i32p, c_f32p]),
     "SLIMB200_ResultToDevice": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "SLIMB200_AssembleModel": (C.c_void_p, [C.c_int32, c_i64p, c_i32p, c_f32p, c_i32p]),

@@ -397,6 +397,12 @@ class ColumnResult:
                                        _ptr(s["rnorm"], C.c_double), _ptr(s["objval"], C.c_double))
         return {k: v[:self.nsel] for k, v in s.items()}
 
+    def phases(self):
+        ph = np.zeros((max(self.nsel, 1), 4), np.float32)
+        ng = np.zeros(max(self.nsel, 1), np.int32)
+        self._lib.SLIMB200_ResultPhases(self.handle, _ptr(ph, C.c_float), _ptr(ng, C.c_int32))
+        return ph[:self.nsel], ng[:self.nsel]
+
     def close(self):
         if getattr(self, "handle", None):
             h = C.c_void_p(self.handle)

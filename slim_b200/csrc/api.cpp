@@ -780,6 +780,11 @@ int32_t SLIMB200_ResultStats(const slimb200_result_t *result, int32_t *niters, i
                       objval);
 }
 
+int32_t SLIMB200_ResultPhases(const slimb200_result_t *result, float *phase_us, int32_t *rounds) {
+  if (!result) return SLIM_ERROR_INPUT;
+  return result_phases(reinterpret_cast<const Result *>(result), phase_us, rounds);
+}
+
 int32_t SLIMB200_ResultToHost(const slimb200_result_t *result, int64_t *colptr, int32_t *colind, float *colval) {
   if (!result) return SLIM_ERROR_INPUT;
   return result_to_host(reinterpret_cast<const Result *>(result), colptr, colind, colval);

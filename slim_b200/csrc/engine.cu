@@ -686,6 +686,8 @@ struct SolveArgs {
   int64_t *st_expand;
   double *st_rnorm;
   double *st_obj;
+  float *st_phase;  // [ntargets][4] microseconds: candidates, active set, sweeps, epilogue (cluster kernel)
+  int32_t *st_ngroups;
 };
 
 template <int NT>
@@ -1071,6 +1073,12 @@ struct CoordView {  // what one CTA needs to know about one coordinate
 };
 
 // The line was written by CTA 0 of the cluster: read it from L2 (ld.global.cg), never from this SM's L1.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ CoordView load_view(const ActMetaC *m, int pr0, int pr1) {
   CoordView v;
   const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(m));      // c0, cnt, aty
@@ -1273,6 +1281,7 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
     const int j = a.targets[q];
     const int64_t cj0 = a.colptr[j];
     const int cntj = a.colcnt[j];
+    const unsigned long long tm0 = globaltimer_ns();
 
     // ---- K1: candidates / aTy by CSR row expansion, all warps of the cluster ------------------------
     long long expand = 0;
@@ -1296,6 +1305,7 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
     }
     __threadfence();
     cl.sync();
+    const unsigned long long tm1 = globaltimer_ns();
 
     // ---- active set, built by CTA 0, read by all ----------------------------------------------------
     long long actnnz = 0;
@@ -1370,6 +1380,7 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
 
     const long long cap64 = 50LL * cntj;
     const int maxit = (int)(cap64 < (long long)a.maxniters ? cap64 : (long long)a.maxniters);
+    const unsigned long long tm2 = globaltimer_ns();
 
     // ---- warm start: yhat slice = sum x_i a_i over this CTA's user range ------------------------------
     if (warm) {
@@ -1614,6 +1625,7 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
       niters = (0.0 < a.opttol) ? 1 : maxit + 1;
     }
 
+    const unsigned long long tm3 = globaltimer_ns();
     // ---- residual / objective over this CTA's user range, then cluster-reduced ------------------------
     double yy = 0.0, yd = 0.0;
     {
@@ -1684,6 +1696,12 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
         const double rn = 0.5 * (yy - 2.0 * yd + hh);
         a.st_rnorm[q] = rn;
         a.st_obj[q] = rn + reg;
+        const unsigned long long tm4 = globaltimer_ns();
+        a.st_phase[4 * q + 0] = (float)((tm1 - tm0) * 1e-3);
+        a.st_phase[4 * q + 1] = (float)((tm2 - tm1) * 1e-3);
+        a.st_phase[4 * q + 2] = (float)((tm3 - tm2) * 1e-3);
+        a.st_phase[4 * q + 3] = (float)((tm4 - tm3) * 1e-3);
+        a.st_ngroups[q] = WINDOW ? sm.ng : na;
       }
       __syncthreads();
     }
@@ -1733,6 +1751,8 @@ struct Result {
   std::vector<int32_t> niters, nactive;
   std::vector<int64_t> actnnz, expand;
   std::vector<double> rnorm, obj;
+  std::vector<float> phase;      // [nsel][4] microseconds (cluster kernel; zeros otherwise)
+  std::vector<int32_t> ngroups;  // sync rounds per sweep
   Timings tm{};
 };
 
@@ -1764,6 +1784,12 @@ int result_stats(const Result *r, int32_t *niters, int32_t *nactive, int64_t *ac
   if (expand_nnz) memcpy(expand_nnz, r->expand.data(), n * sizeof(int64_t));
   if (rnorm) memcpy(rnorm, r->rnorm.data(), n * sizeof(double));
   if (objval) memcpy(objval, r->obj.data(), n * sizeof(double));
+  return kOk;
+}
+
+int result_phases(const Result *r, float *phase_us, int32_t *ngroups) {
+  if (phase_us) memcpy(phase_us, r->phase.data(), sizeof(float) * r->phase.size());
+  if (ngroups) memcpy(ngroups, r->ngroups.data(), sizeof(int32_t) * r->ngroups.size());
   return kOk;
 }
 
@@ -1909,6 +1935,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     res->expand.assign(nsel, 0);
     res->rnorm.assign(nsel, 0.0);
     res->obj.assign(nsel, 0.0);
+    res->phase.assign((size_t)nsel * 4, 0.f);
+    res->ngroups.assign(nsel, 0);
 
     // processing order: heaviest target column first (longest-processing-time-first on the queue)
     std::vector<int32_t> order(nsel);
@@ -2086,6 +2114,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         DevBuf<int32_t> d_targets, d_queue, d_ocnt, d_nit, d_nact;
         DevBuf<int64_t> d_ooff, d_an, d_ex;
         DevBuf<double> d_rn, d_ob;
+        DevBuf<float> d_ph;
+        DevBuf<int32_t> d_ng;
         DevBuf<unsigned long long> d_used;
         d_targets.alloc(nt);
         d_queue.alloc_zero(1, s);
@@ -2098,6 +2128,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         d_ex.alloc(nt);
         d_rn.alloc(nt);
         d_ob.alloc(nt);
+        d_ph.alloc_zero((size_t)nt * 4, s);
+        d_ng.alloc_zero(nt, s);
         Pool pl{nullptr, nullptr};
         CK(cudaMalloc(&pl.idx, sizeof(int32_t) * cap));
         pools.push_back(pl);
@@ -2118,6 +2150,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         args.st_expand = d_ex.p;
         args.st_rnorm = d_rn.p;
         args.st_obj = d_ob.p;
+        args.st_phase = d_ph.p;
+        args.st_ngroups = d_ng.p;
         LaunchPlan lp = plan;
         lp.grid = std::min(plan.grid, nt);
         CK(cudaEventRecord(e0, s));
@@ -2134,6 +2168,10 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         std::vector<int32_t> h_cnt(nt), h_nit(nt), h_nact(nt);
         std::vector<int64_t> h_off(nt), h_an(nt), h_ex(nt);
         std::vector<double> h_rn(nt), h_ob(nt);
+        std::vector<float> h_ph((size_t)nt * 4);
+        std::vector<int32_t> h_ng(nt);
+        CK(cudaMemcpyAsync(h_ph.data(), d_ph.p, sizeof(float) * nt * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_ng.data(), d_ng.p, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(h_cnt.data(), d_ocnt.p, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(h_off.data(), d_ooff.p, sizeof(int64_t) * nt, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(h_nit.data(), d_nit.p, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, s));
@@ -2156,6 +2194,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
           res->expand[q] = h_ex[k];
           res->rnorm[q] = h_rn[k];
           res->obj[q] = h_ob[k];
+          for (int z = 0; z < 4; z++) res->phase[(size_t)q * 4 + z] = h_ph[(size_t)k * 4 + z];
+          res->ngroups[q] = h_ng[k];
           if (h_cnt[k] >= 0) {
             cnt[q] = h_cnt[k];
             src_off[q] = h_off[k];

@@ -56,6 +56,9 @@ void result_info(const Result *r, int32_t *nsel, int64_t *nnz, Timings *t);
 // Per-column statistics in the caller's column order; any pointer may be null.
 int result_stats(const Result *r, int32_t *niters, int32_t *nactive, int64_t *active_nnz,
                  int64_t *expand_nnz, double *rnorm, double *objval);
+// Per-column phase times of the cluster kernel in microseconds [nsel][4] (candidates, active set,
+// sweeps, epilogue) and the number of barrier rounds per sweep; zeros for the team kernel.
+int result_phases(const Result *r, float *phase_us, int32_t *ngroups);
 int result_to_host(const Result *r, int64_t *colptr, int32_t *colind, float *colval);
 // Same, into caller-owned DEVICE buffers on the matrix's device (counts int32[nsel]).
 int result_to_device(const Result *r, int32_t *d_counts, int32_t *d_colind, float *d_colval);
