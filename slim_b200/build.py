@@ -41,7 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not stale():
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("SLIMB200_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", str(LIB)] + [str(s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:

@@ -1136,16 +1136,96 @@ struct ClusterSmem {
   long long off;
 };
 
-struct __align__(16) WindowSmem {  // window sweep only
-  double G[32][32];                // Gram block of the window, G[m][k] = <a_m, a_k>
-  double pall[2][kParts][32];      // per-CTA partial inner products of every CTA (DSMEM exchange)
-  double pcta[32];                 // this CTA's partial inner product per window slot
-  double pw[kClusterNT / 32];
-  double dlt[32];                  // yhat step per window slot
-  long long c0[32];
-  int s0[32], s1[32];
-  double dl;
+// ---- window sweep: shared-memory pipeline --------------------------------------------------------
+// Static description of one round (= one 32-item window) for THIS CTA, built one round ahead of its
+// copies and two rounds ahead of its use by the producer warp.
+struct __align__(16) RoundTab {
+  long long c0[32];   // padded offset of the column of slot b
+  double inv_den[32]; // 1 / (cnorm^2 + l2r)
+  double sq[32];      // exact sum of squares
+  int s0[32], s1[32]; // this CTA's entry range in the column
+  int soff[32];       // first 16-byte chunk of the staged copy in the stage buffer, -1: not staged
+  int p[32];          // position in the active list (x[p])
+  float aty[32];
+  unsigned mask;      // active slots
+  int win;            // window id
+  unsigned bytes;     // bytes of column data staged for the round
+  int pad;
 };
+
+template <bool HASVAL>
+struct __align__(128) PipeSmem {
+  static constexpr int CAP = HASVAL ? 1536 : 3072;  // 16-byte chunks per stage buffer
+  uint4 sidx[2][CAP];                               // staged user ids of the round's small columns
+  float4 sval[HASVAL ? 2 : 1][HASVAL ? CAP : 1];    // ... and their values
+  double G[2][32][32];                              // Gram block of the window, G[m][k] = <a_m, a_k>
+  double pall[2][kParts][32];                       // partial inner products of every CTA (DSMEM exchange)
+  RoundTab tab[3];
+  double pcta[32];                                  // this CTA's partial inner product per slot
+  double dlt[32];                                   // yhat step per slot
+  double pw[kClusterNT / 32];
+  double dl;
+  unsigned long long mbar[2];                       // "stage buffer b has landed"
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// <a, yhat> / yhat += d a over a STAGED column range: user ids (and values) come from shared memory
+template <bool HASVAL>
+__device__ __forceinline__ double warp_dot_staged(const uint4 *sidx, const float4 *sval, int s0, int s1,
+                                                  const double *yh) {
+  const int lane = threadIdx.x & 31;
+  const int ch0 = s0 >> 2, nch = ((s1 + 3) >> 2) - ch0;
+  double part = 0.0;
+#pragma unroll 2
+  for (int k = lane; k < nch; k += 32) {
+    Chunk c;
+    c.ix = sidx[k];
+    if (HASVAL) c.vv = sval[k];
+    part += dot_chunk_r<HASVAL, true>(c, (ch0 + k) * 4, s0, s1, yh);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  return part;
+}
+
+template <bool HASVAL>
+__device__ __forceinline__ void warp_axpy_staged(const uint4 *sidx, const float4 *sval, int s0, int s1, double d,
+                                                 double *yh) {
+  const int lane = threadIdx.x & 31;
+  const int ch0 = s0 >> 2, nch = ((s1 + 3) >> 2) - ch0;
+#pragma unroll 2
+  for (int k = lane; k < nch; k += 32) {
+    Chunk c;
+    c.ix = sidx[k];
+    if (HASVAL) c.vv = sval[k];
+    axpy_chunk_r<HASVAL, true>(c, (ch0 + k) * 4, s0, s1, d, yh);
+  }
+}
 
 // <a, yhat> over entries [s0, s1) of a column, one warp (lanes stride the 16-byte chunks)
 template <bool HASVAL>
@@ -1245,11 +1325,25 @@ __device__ __forceinline__ double cluster_sum(double v, ClusterSmem &sm, int &pa
   return tot;
 }
 
+#ifdef SLIM_PROFILE_ROUNDS
+#define SLIM_TICK(k)                          \
+  do {                                        \
+    const long long now_ = clock64();         \
+    prof[k] += now_ - tick_;                  \
+    tick_ = now_;                             \
+  } while (0)
+#else
+#define SLIM_TICK(k) do { } while (0)
+#endif
+
 template <bool HASVAL, bool WINDOW>
 __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveArgs a, const ClusterArgs ca) {
   constexpr int NT = kClusterNT, NW = NT / 32;
+  constexpr int NCW = NW - 1;  // consumer warps of the window sweep (the last warp is the producer)
   __shared__ ClusterSmem sm;
-  __shared__ WindowSmem ws;
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  PipeSmem<HASVAL> &ps = *reinterpret_cast<PipeSmem<HASVAL> *>(dyn_smem);
+  unsigned rr = 0;  // rounds consumed so far by this CTA (kernel lifetime): buffer rr&1, parity (rr>>1)&1
   cg::cluster_group cl = cg::this_cluster();
   const int cs = (int)cl.num_blocks();
   const int rank = (int)cl.block_rank();
@@ -1268,6 +1362,16 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
   GroupMeta *groups = ca.groups + (size_t)cid * ca.grp_stride;
   double *x = ca.xc + (size_t)blockIdx.x * a.col_stride;
   double *yh = a.yhat + (size_t)cid * a.row_stride;
+
+  if (WINDOW) {
+    if (tid == 0) {
+      mbar_init(&ps.mbar[0], 1);
+      mbar_init(&ps.mbar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      fence_proxy_async();
+    }
+    __syncthreads();
+  }
 
   for (;;) {
     // ---- next target -----------------------------------------------------------------------------
@@ -1406,130 +1510,220 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
       // coordinates m < k of the window:  <a_k, yhat_0> + sum_{m<k} d_m <a_k, a_m>.  The first term comes
       // from ONE pass over the window's columns against the yhat at the start of the round, the second
       // from the precomputed Gram block, so a round costs one cluster barrier for up to 32 coordinates.
+      //
+      // Software pipeline: everything a round needs that does not depend on yhat -- its slot table, the
+      // user ids of its columns inside this CTA's user range, its Gram block -- is brought into shared
+      // memory while the previous round runs: the producer warp builds the table two rounds ahead and
+      // issues TMA bulk copies (cp.async.bulk, completion on an mbarrier) one round ahead.  On the
+      // critical path of a round remain: the yhat gather (L2), the exchange of 32 partials through
+      // DSMEM + one cluster barrier, the Gram-space solve, and the yhat update.
+      constexpr int CAP = PipeSmem<HASVAL>::CAP;
       const int ng = sm.ng;
+
+      auto build_tab = [&](int r) {  // producer warp: slot table of local round r
+        RoundTab &T = ps.tab[r % 3];
+        const int4 gm = __ldcg(reinterpret_cast<const int4 *>(groups + (r % ng)));
+        const unsigned mask = (unsigned)gm.y;
+        const bool act = (mask >> lane) & 1u;
+        int nch = 0;
+        bool small = false;
+        if (act) {
+          const int p = gm.z + __popc(mask & ((1u << lane) - 1u));
+          const CoordView v = load_view(&meta[p], pr0, pr1);
+          T.c0[lane] = v.c0;
+          T.s0[lane] = v.s0;
+          T.s1[lane] = v.s1;
+          T.p[lane] = p;
+          T.aty[lane] = v.aty;
+          T.inv_den[lane] = 1.0 / v.den;
+          T.sq[lane] = v.sq;
+          nch = ((v.s1 + 3) >> 2) - (v.s0 >> 2);
+          small = (v.s1 > v.s0) && (v.s1 - v.s0 <= kSmallCol);
+        }
+        int want = small ? nch : 0, pre = want;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, pre, o);
+          if (lane >= o) pre += up;
+        }
+        const bool staged = small && pre <= CAP;  // pre is the inclusive prefix
+        T.soff[lane] = staged ? pre - want : -1;
+        int tot = staged ? nch : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) {
+          T.mask = mask;
+          T.win = gm.x;
+          T.bytes = (unsigned)tot * (HASVAL ? 32u : 16u);
+        }
+        __syncwarp();
+      };
+      auto issue_copies = [&](int r, unsigned buf) {  // producer warp: stage local round r into buffer buf
+        const RoundTab &T = ps.tab[r % 3];
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(&ps.mbar[buf], T.bytes + 8192u);
+        __syncwarp();
+        if (((T.mask >> lane) & 1u) && T.soff[lane] >= 0) {
+          const int ch0 = T.s0[lane] >> 2, nch = ((T.s1[lane] + 3) >> 2) - ch0;
+          bulk_g2s(&ps.sidx[buf][T.soff[lane]], a.colind + T.c0[lane] + 4 * (int64_t)ch0, (uint32_t)nch * 16u,
+                   &ps.mbar[buf]);
+          if (HASVAL)
+            bulk_g2s(&ps.sval[buf][T.soff[lane]], a.colval + T.c0[lane] + 4 * (int64_t)ch0, (uint32_t)nch * 16u,
+                     &ps.mbar[buf]);
+        }
+        if (lane == 0) bulk_g2s(&ps.G[buf][0][0], ca.wgram + (size_t)T.win * 1024, 8192u, &ps.mbar[buf]);
+      };
+
+      // prologue: tables of rounds 0 and 1, copies of round 0
+      if (warp == NW - 1) {
+        build_tab(0);
+        build_tab(1);
+        issue_copies(0, rr & 1u);
+      } else if (warp == 0) {
+        ps.pcta[lane] = 0.0;
+      }
+      __syncthreads();
+
       bool done = false;
-      int t = 0;
+      int t = 0, r = 0;
+#ifdef SLIM_PROFILE_ROUNDS
+      long long prof[5] = {0, 0, 0, 0, 0};
+      long long tick_ = clock64();
+#endif
       for (; t < maxit && !done; t++) {
         double dltx = 0.0;
-        for (int g = 0; g < ng; g++) {
-          const int4 gm = __ldcg(reinterpret_cast<const int4 *>(groups + g));
-          const int win = gm.x;
-          const unsigned mask = (unsigned)gm.y;
-          const int pbase = gm.z;
-          float r_aty = 0.f;
-          double r_den = 1.0, r_sq = 0.0;
-          int r_p = 0;
-          if (tid < 32) {
-            if ((mask >> tid) & 1u) {
-              r_p = pbase + __popc(mask & ((1u << tid) - 1u));
-              const CoordView v = load_view(&meta[r_p], pr0, pr1);
-              ws.c0[tid] = v.c0;
-              ws.s0[tid] = v.s0;
-              ws.s1[tid] = v.s1;
-              r_aty = v.aty;
-              r_den = v.den;
-              r_sq = v.sq;
-            }
-            ws.pcta[tid] = 0.0;
+        for (int g = 0; g < ng; g++, r++, rr++) {
+          const unsigned buf = rr & 1u;
+          const RoundTab &T = ps.tab[r % 3];
+          const unsigned mask = T.mask;
+          double xi = 0.0;
+          if (warp == 0 && ((mask >> lane) & 1u)) xi = x[T.p[lane]];  // consumed by the solve
+          if (warp == NW - 1) {
+            // runs beside the consumers' gather; joins them at the barrier after it
+            issue_copies(r + 1, buf ^ 1u);  // next round's columns + Gram block
+            build_tab(r + 2);               // and the table of the round after it
           }
-          reinterpret_cast<double2 *>(&ws.G[0][0])[tid] =
-              __ldg(reinterpret_cast<const double2 *>(ca.wgram + (size_t)win * 1024) + tid);
-          __syncthreads();
+          mbar_wait(&ps.mbar[buf], (rr >> 1) & 1u);  // this round's staged data has landed
+          SLIM_TICK(0);
 
-          // gather: small columns one warp each, large columns by the whole CTA
+          // gather: staged small columns from shared memory, one consumer warp each; the rest from global
           {
             int ord = 0;
             for (unsigned mm = mask; mm; mm &= mm - 1) {
               const int b = __ffs(mm) - 1;
-              const int s0 = ws.s0[b], s1 = ws.s1[b];
+              const int s0 = T.s0[b], s1 = T.s1[b];
               if (s1 - s0 <= kSmallCol) {
-                if ((ord & (NW - 1)) == warp) {
-                  const double v = warp_dot<HASVAL>(a, ws.c0[b], s0, s1, yh);
-                  if (lane == 0) ws.pcta[b] = v;
+                if (ord == warp || ord == warp + NCW || ord == warp + 2 * NCW) {
+                  if (warp < NCW && s1 > s0) {
+                    const int so = T.soff[b];
+                    const double v = so >= 0 ? warp_dot_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, yh)
+                                             : warp_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
+                    if (lane == 0) ps.pcta[b] = v;
+                  }
                 }
                 ord++;
               }
             }
             for (unsigned mm = mask; mm; mm &= mm - 1) {
               const int b = __ffs(mm) - 1;
-              const int s0 = ws.s0[b], s1 = ws.s1[b];
+              const int s0 = T.s0[b], s1 = T.s1[b];
               if (s1 - s0 > kSmallCol) {
-                double v = block_dot<HASVAL>(a, ws.c0[b], s0, s1, yh);
+                double v = block_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) ws.pw[warp] = v;
+                if (lane == 0) ps.pw[warp] = v;
                 __syncthreads();
                 if (tid == 0) {
                   double sum = 0.0;
 #pragma unroll
-                  for (int i = 0; i < NW; i++) sum += ws.pw[i];
-                  ws.pcta[b] = sum;
+                  for (int i = 0; i < NW; i++) sum += ps.pw[i];
+                  ps.pcta[b] = sum;
                 }
                 __syncthreads();
               }
             }
           }
           __syncthreads();
+          SLIM_TICK(1);
           {
             const int dst = tid >> 5, b = tid & 31;
-            if (dst < cs) *cl.map_shared_rank(&ws.pall[par][rank][b], dst) = ws.pcta[b];
+            if (dst < cs) *cl.map_shared_rank(&ps.pall[par][rank][b], dst) = ps.pcta[b];
           }
           cl.sync();
+          SLIM_TICK(2);
 
           // Gram-space sequential solve of the window by warp 0 (identical in every CTA)
           if (warp == 0) {
             const bool act = (mask >> lane) & 1u;
             double P = 0.0;
             if (act)
-              for (int c = 0; c < cs; c++) P += ws.pall[par][c][lane];
-            const double xi = act ? x[r_p] : 0.0;
+              for (int c = 0; c < cs; c++) P += ps.pall[par][c][lane];
             const double in_old = fabs(xi) > kEps ? xi : 0.0;
-            double ip = P - in_old * r_sq;
+            const double aty = act ? (double)T.aty[lane] : 0.0;
+            const double inv_den = act ? T.inv_den[lane] : 0.0;
+            double ip = P - in_old * (act ? T.sq[lane] : 0.0);
             double nx = xi, d = 0.0;
             for (unsigned mm = mask; mm; mm &= mm - 1) {
               const int mb = __ffs(mm) - 1;
               double dm = 0.0;
               if (lane == mb) {
-                const double num = (double)r_aty - ip;
-                nx = num > a.l1r ? (num - a.l1r) / r_den : 0.0;
+                const double num = aty - ip;
+                nx = num > a.l1r ? (num - a.l1r) * inv_den : 0.0;
                 const double in_new = fabs(nx) > kEps ? nx : 0.0;
                 d = in_new - in_old;
                 dm = d;
               }
               dm = __shfl_sync(0xffffffffu, dm, mb);
-              if (dm != 0.0 && act && lane > mb) ip += dm * ws.G[mb][lane];
+              if (dm != 0.0 && act && lane > mb) ip += dm * ps.G[buf][mb][lane];
             }
-            if (act) x[r_p] = nx;
-            ws.dlt[lane] = act ? d : 0.0;
+            if (act) x[T.p[lane]] = nx;
+            ps.dlt[lane] = act ? d : 0.0;
             double dd = act ? (nx - xi) * (nx - xi) : 0.0;
 #pragma unroll
             for (int o = 16; o; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
-            if (lane == 0) ws.dl = dd;
+            if (lane == 0) ps.dl = dd;
+          } else if (warp == 1) {
+            ps.pcta[lane] = 0.0;  // every CTA has read the partials (cluster barrier above): clear for the next round
           }
           __syncthreads();
-          dltx += ws.dl;
+          SLIM_TICK(3);
+          dltx += ps.dl;
 
-          // update this CTA's yhat slice: yhat += sum_k d_k a_k
+          // update this CTA's yhat slice: yhat += sum_k d_k a_k  (fp64 atomics: columns may share users)
           {
             int ord = 0;
             for (unsigned mm = mask; mm; mm &= mm - 1) {
               const int b = __ffs(mm) - 1;
-              const int s0 = ws.s0[b], s1 = ws.s1[b];
-              const double d = ws.dlt[b];
+              const int s0 = T.s0[b], s1 = T.s1[b];
+              const double d = ps.dlt[b];
               if (s1 - s0 <= kSmallCol) {
-                if ((ord & (NW - 1)) == warp && d != 0.0) warp_axpy<HASVAL>(a, ws.c0[b], s0, s1, d, yh);
+                if ((ord == warp || ord == warp + NCW || ord == warp + 2 * NCW) && warp < NCW && d != 0.0 && s1 > s0) {
+                  const int so = T.soff[b];
+                  if (so >= 0) warp_axpy_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, d, yh);
+                  else warp_axpy<HASVAL>(a, T.c0[b], s0, s1, d, yh);
+                }
                 ord++;
               } else if (d != 0.0) {
-                block_axpy<HASVAL>(a, ws.c0[b], s0, s1, d, yh);
+                block_axpy<HASVAL>(a, T.c0[b], s0, s1, d, yh);
               }
             }
           }
           __syncthreads();
+          SLIM_TICK(4);
           par ^= 1;
         }
         if (dltx < a.opttol) done = true;
       }
       niters = done ? t : maxit + 1;
+      // drain the copies issued for the round that will not run, so the barrier phases stay in step
+      mbar_wait(&ps.mbar[rr & 1u], (rr >> 1) & 1u);
+      rr++;
+      __syncthreads();
+#ifdef SLIM_PROFILE_ROUNDS
+      if (rank == 0 && tid == 0)
+        printf("target %d na %d ng %d sweeps %d cycles: meta %lld gather %lld exchange %lld solve %lld update %lld\n",
+               j, na, ng, t, prof[0], prof[1], prof[2], prof[3], prof[4]);
+#endif
     } else if (na > 0 && maxit > 0) {
       CoordView v_cur = load_view(&meta[0], pr0, pr1);
       CoordView v_nxt = load_view(&meta[na > 1 ? 1 : 0], pr0, pr1);
@@ -1869,7 +2063,9 @@ template <bool HASVAL, bool WINDOW>
 static int cluster_launch(const SolveArgs &args, const ClusterArgs &cargs, int cs, int nclusters, cudaStream_t s,
                           bool query_only) {
   auto kern = cd_cluster_kernel<HASVAL, WINDOW>;
+  const size_t dyn = WINDOW ? sizeof(PipeSmem<HASVAL>) : 0;
   if (cs > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  if (dyn) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1878,7 +2074,7 @@ static int cluster_launch(const SolveArgs &args, const ClusterArgs &cargs, int c
   attr[0].val.clusterDim.z = 1;
   cfg.gridDim = dim3((unsigned)(cs * std::max(nclusters, 1)), 1, 1);
   cfg.blockDim = dim3(kClusterNT, 1, 1);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = dyn;
   cfg.stream = s;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
