@@ -1520,25 +1520,42 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
       constexpr int CAP = PipeSmem<HASVAL>::CAP;
       const int ng = sm.ng;
 
-      auto build_tab = [&](int r) {  // producer warp: slot table of local round r
-        RoundTab &T = ps.tab[r % 3];
-        const int4 gm = __ldcg(reinterpret_cast<const int4 *>(groups + (r % ng)));
+      // Producer warp, slot table of local round r, split in two phases so that its two dependent L2
+      // reads never sit on a round's critical path: tab_load() issues the reads of the coordinate lines
+      // (given the window record read one round earlier), tab_store() consumes them a round later.
+      struct TabRegs {
+        int4 gm;          // window record: id, active mask, first position
+        int4 h0, h1;      // coordinate line of slot `lane`
+        int sp0, sp1;
+      };
+      auto tab_load = [&](const int4 gm, TabRegs &R) {
+        R.gm = gm;
         const unsigned mask = (unsigned)gm.y;
+        if ((mask >> lane) & 1u) {
+          const ActMetaC *m = &meta[gm.z + __popc(mask & ((1u << lane) - 1u))];
+          R.h0 = __ldcg(reinterpret_cast<const int4 *>(m));
+          R.h1 = __ldcg(reinterpret_cast<const int4 *>(m) + 1);
+          R.sp0 = __ldcg(&m->split[pr0]);
+          R.sp1 = __ldcg(&m->split[pr1]);
+        }
+      };
+      auto tab_store = [&](int r, const TabRegs &R) {
+        RoundTab &T = ps.tab[r % 3];
+        const unsigned mask = (unsigned)R.gm.y;
         const bool act = (mask >> lane) & 1u;
         int nch = 0;
         bool small = false;
         if (act) {
-          const int p = gm.z + __popc(mask & ((1u << lane) - 1u));
-          const CoordView v = load_view(&meta[p], pr0, pr1);
-          T.c0[lane] = v.c0;
-          T.s0[lane] = v.s0;
-          T.s1[lane] = v.s1;
-          T.p[lane] = p;
-          T.aty[lane] = v.aty;
-          T.inv_den[lane] = 1.0 / v.den;
-          T.sq[lane] = v.sq;
-          nch = ((v.s1 + 3) >> 2) - (v.s0 >> 2);
-          small = (v.s1 > v.s0) && (v.s1 - v.s0 <= kSmallCol);
+          const double den = __hiloint2double(R.h1.y, R.h1.x);
+          T.c0[lane] = (long long)(((unsigned long long)(unsigned)R.h0.y << 32) | (unsigned)R.h0.x);
+          T.s0[lane] = R.sp0;
+          T.s1[lane] = R.sp1;
+          T.p[lane] = R.gm.z + __popc(mask & ((1u << lane) - 1u));
+          T.aty[lane] = __int_as_float(R.h0.w);
+          T.inv_den[lane] = 1.0 / den;
+          T.sq[lane] = __hiloint2double(R.h1.w, R.h1.z);
+          nch = ((R.sp1 + 3) >> 2) - (R.sp0 >> 2);
+          small = (R.sp1 > R.sp0) && (R.sp1 - R.sp0 <= kSmallCol);
         }
         int want = small ? nch : 0, pre = want;
 #pragma unroll
@@ -1553,11 +1570,12 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
         for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (lane == 0) {
           T.mask = mask;
-          T.win = gm.x;
+          T.win = R.gm.x;
           T.bytes = (unsigned)tot * (HASVAL ? 32u : 16u);
         }
         __syncwarp();
       };
+      auto group_rec = [&](int r) { return __ldcg(reinterpret_cast<const int4 *>(groups + (r % ng))); };
       auto issue_copies = [&](int r, unsigned buf) {  // producer warp: stage local round r into buffer buf
         const RoundTab &T = ps.tab[r % 3];
         fence_proxy_async();
@@ -1575,10 +1593,15 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
       };
 
       // prologue: tables of rounds 0 and 1, copies of round 0
+      TabRegs treg;     // producer warp: coordinate lines of round r + 2 in flight
+      int4 gm_ahead = make_int4(0, 0, 0, 0);  // window record of round r + 3
       if (warp == NW - 1) {
-        build_tab(0);
-        build_tab(1);
+        tab_load(group_rec(0), treg);
+        tab_store(0, treg);
+        tab_load(group_rec(1), treg);
+        tab_store(1, treg);
         issue_copies(0, rr & 1u);
+        gm_ahead = group_rec(2);
       } else if (warp == 0) {
         ps.pcta[lane] = 0.0;
       }
@@ -1599,29 +1622,77 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
           double xi = 0.0;
           if (warp == 0 && ((mask >> lane) & 1u)) xi = x[T.p[lane]];  // consumed by the solve
           if (warp == NW - 1) {
-            // runs beside the consumers' gather; joins them at the barrier after it
-            issue_copies(r + 1, buf ^ 1u);  // next round's columns + Gram block
-            build_tab(r + 2);               // and the table of the round after it
+            issue_copies(r + 1, buf ^ 1u);  // next round's columns + Gram block (tables are one round ahead)
+            tab_load(gm_ahead, treg);       // start reading the coordinate lines of round r + 2 ...
+            gm_ahead = group_rec(r + 3);    // ... and the window record of round r + 3
           }
           mbar_wait(&ps.mbar[buf], (rr >> 1) & 1u);  // this round's staged data has landed
           SLIM_TICK(0);
 
           // gather: staged small columns from shared memory, one consumer warp each; the rest from global
           {
-            int ord = 0;
-            for (unsigned mm = mask; mm; mm &= mm - 1) {
-              const int b = __ffs(mm) - 1;
-              const int s0 = T.s0[b], s1 = T.s1[b];
-              if (s1 - s0 <= kSmallCol) {
-                if (ord == warp || ord == warp + NCW || ord == warp + 2 * NCW) {
-                  if (warp < NCW && s1 > s0) {
-                    const int so = T.soff[b];
-                    const double v = so >= 0 ? warp_dot_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, yh)
-                                             : warp_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
-                    if (lane == 0) ps.pcta[b] = v;
-                  }
+            // slots of this warp: the ord-th small column goes to consumer warp ord % NCW
+            int myb0 = -1, myb1 = -1, myb2 = -1;
+            {
+              int ord = 0;
+              for (unsigned mm = mask; mm; mm &= mm - 1) {
+                const int b = __ffs(mm) - 1;
+                if (T.s1[b] - T.s0[b] <= kSmallCol) {
+                  if (ord == warp) myb0 = b;
+                  else if (ord == warp + NCW) myb1 = b;
+                  else if (ord == warp + 2 * NCW) myb2 = b;
+                  ord++;
                 }
-                ord++;
+              }
+            }
+            if (warp < NCW && myb0 >= 0) {
+              // fast path: every column of this warp is staged with at most one 16-byte chunk per lane --
+              // all yhat gathers (L2 latency) are issued before the first reduction
+              auto one_chunk = [&](int b) {
+                return b < 0 || (T.soff[b] >= 0 && ((T.s1[b] + 3) >> 2) - (T.s0[b] >> 2) <= 32) || T.s1[b] <= T.s0[b];
+              };
+              if (one_chunk(myb0) && one_chunk(myb1) && one_chunk(myb2)) {
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+                auto part_of = [&](int b) {
+                  double v = 0.0;
+                  if (b >= 0 && T.s1[b] > T.s0[b]) {
+                    const int s0 = T.s0[b], s1 = T.s1[b], ch0 = s0 >> 2, nch = ((s1 + 3) >> 2) - ch0;
+                    if (lane < nch) {
+                      Chunk c;
+                      c.ix = ps.sidx[buf][T.soff[b] + lane];
+                      if (HASVAL) c.vv = ps.sval[HASVAL ? buf : 0][HASVAL ? T.soff[b] + lane : 0];
+                      v = dot_chunk_r<HASVAL, true>(c, (ch0 + lane) * 4, s0, s1, yh);
+                    }
+                  }
+                  return v;
+                };
+                p0 = part_of(myb0);
+                p1 = part_of(myb1);
+                p2 = part_of(myb2);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                  p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+                  p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                  p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+                }
+                if (lane == 0) {
+                  ps.pcta[myb0] = p0;
+                  if (myb1 >= 0) ps.pcta[myb1] = p1;
+                  if (myb2 >= 0) ps.pcta[myb2] = p2;
+                }
+              } else {
+                const int mine[3] = {myb0, myb1, myb2};
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                  const int b = mine[k];
+                  if (b < 0) continue;
+                  const int s0 = T.s0[b], s1 = T.s1[b];
+                  if (s1 <= s0) continue;
+                  const int so = T.soff[b];
+                  const double v = so >= 0 ? warp_dot_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, yh)
+                                           : warp_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
+                  if (lane == 0) ps.pcta[b] = v;
+                }
               }
             }
             for (unsigned mm = mask; mm; mm &= mm - 1) {
@@ -1708,6 +1779,7 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
               }
             }
           }
+          if (warp == NW - 1) tab_store(r + 2, treg);  // ... consumed here, a whole round later
           __syncthreads();
           SLIM_TICK(4);
           par ^= 1;
