@@ -1122,7 +1122,12 @@ __device__ __forceinline__ void axpy_chunk_r(const Chunk &r, int e0, int lo, int
 #undef SLIM_UPD
 }
 
-constexpr int kClusterNT = 512;
+#ifndef SLIM_CLUSTER_NT
+#define SLIM_CLUSTER_NT 256
+#endif
+constexpr int kClusterNT = SLIM_CLUSTER_NT;                 // threads per CTA of the cluster kernel
+constexpr int kClusterCtasPerSm = kClusterNT <= 256 ? 2 : 1;  // two co-resident CTAs interleave their rounds
+constexpr int kWarpSlots = 5;  // small columns of a round per consumer warp: ceil(32 / (kClusterNT/32 - 1))
 
 constexpr int kSmallCol = 4096;  // entries of a column inside one CTA's user range handled by ONE warp
 
@@ -1147,25 +1152,30 @@ struct __align__(16) RoundTab {
   int soff[32];       // first 16-byte chunk of the staged copy in the stage buffer, -1: not staged
   int p[32];          // position in the active list (x[p])
   float aty[32];
+  signed char wslot[kClusterNT / 32][8];  // the (up to kWarpSlots) small columns gathered by consumer warp w, -1: none
+  signed char abit[32];                   // active slots in ascending order (the solve's visiting order)
   unsigned mask;      // active slots
+  unsigned bigmask;   // active slots whose range is too long for one warp: gathered by the whole CTA
   int win;            // window id
   unsigned bytes;     // bytes of column data staged for the round
-  int pad;
+  int nact;
+  int pad[3];
 };
 
 template <bool HASVAL>
 struct __align__(128) PipeSmem {
-  static constexpr int CAP = HASVAL ? 1536 : 3072;  // 16-byte chunks per stage buffer
+  static constexpr int CAP = (HASVAL ? 1536 : 3072) / kClusterCtasPerSm;  // 16-byte chunks per stage buffer
   uint4 sidx[2][CAP];                               // staged user ids of the round's small columns
   float4 sval[HASVAL ? 2 : 1][HASVAL ? CAP : 1];    // ... and their values
   double G[2][32][32];                              // Gram block of the window, G[m][k] = <a_m, a_k>
   double pall[2][kParts][32];                       // partial inner products of every CTA (DSMEM exchange)
   RoundTab tab[3];
-  double pcta[32];                                  // this CTA's partial inner product per slot
+  double pcta[2][32];                               // this CTA's partial inner products per slot (per exchange buffer)
   double dlt[32];                                   // yhat step per slot
   double pw[kClusterNT / 32];
   double dl;
   unsigned long long mbar[2];                       // "stage buffer b has landed"
+  unsigned long long xbar[2];                       // "all CTAs' partials of exchange buffer b have landed"
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1190,6 +1200,28 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// Remote (DSMEM) 8-byte store that signals an mbarrier in the DESTINATION CTA: the exchange of the
+// per-CTA partial inner products needs no cluster-wide barrier, each CTA just waits on its own mbarrier.
+__device__ __forceinline__ void st_async_peer(void *local_dst, unsigned long long *local_bar, uint32_t peer_rank,
+                                              double v) {
+  uint32_t rdst, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(local_dst)), "r"(peer_rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar)), "r"(peer_rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(rdst),
+               "l"(__double_as_longlong(v)), "r"(rbar)
+               : "memory");
+}
+// Bulk copy from this CTA's shared memory into a peer CTA's shared memory, completion (bytes) counted
+// on the PEER's mbarrier: one message and one barrier update per destination.
+__device__ __forceinline__ void bulk_s2peer(void *local_dst, const void *local_src, uint32_t bytes,
+                                            unsigned long long *local_bar, uint32_t peer_rank) {
+  uint32_t rdst, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(local_dst)), "r"(peer_rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar)), "r"(peer_rank));
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rdst),
+               "r"(smem_u32(local_src)), "r"(bytes), "r"(rbar)
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -1337,13 +1369,14 @@ __device__ __forceinline__ double cluster_sum(double v, ClusterSmem &sm, int &pa
 #endif
 
 template <bool HASVAL, bool WINDOW>
-__global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveArgs a, const ClusterArgs ca) {
+__global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kernel(const SolveArgs a, const ClusterArgs ca) {
   constexpr int NT = kClusterNT, NW = NT / 32;
   constexpr int NCW = NW - 1;  // consumer warps of the window sweep (the last warp is the producer)
   __shared__ ClusterSmem sm;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   PipeSmem<HASVAL> &ps = *reinterpret_cast<PipeSmem<HASVAL> *>(dyn_smem);
   unsigned rr = 0;  // rounds consumed so far by this CTA (kernel lifetime): buffer rr&1, parity (rr>>1)&1
+  unsigned xr = 0;  // exchanges done so far (kernel lifetime): buffer xr&1, parity (xr>>1)&1
   cg::cluster_group cl = cg::this_cluster();
   const int cs = (int)cl.num_blocks();
   const int rank = (int)cl.block_rank();
@@ -1367,6 +1400,8 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
     if (tid == 0) {
       mbar_init(&ps.mbar[0], 1);
       mbar_init(&ps.mbar[1], 1);
+      mbar_init(&ps.xbar[0], 1);
+      mbar_init(&ps.xbar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       fence_proxy_async();
     }
@@ -1565,13 +1600,25 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
         }
         const bool staged = small && pre <= CAP;  // pre is the inclusive prefix
         T.soff[lane] = staged ? pre - want : -1;
+        // work lists: the ord-th small column goes to consumer warp ord % NCW; big columns to the whole CTA
+        for (int k = lane; k < 8 * NW; k += 32) (&T.wslot[0][0])[k] = -1;
+        __syncwarp();
+        const unsigned smask = __ballot_sync(0xffffffffu, small);
+        const unsigned bmask = __ballot_sync(0xffffffffu, act && !small && R.sp1 > R.sp0);
+        if (small) {
+          const int ord = __popc(smask & ((1u << lane) - 1u));
+          T.wslot[ord % NCW][ord / NCW] = (signed char)lane;
+        }
+        if (act) T.abit[__popc(mask & ((1u << lane) - 1u))] = (signed char)lane;
         int tot = staged ? nch : 0;
 #pragma unroll
         for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (lane == 0) {
           T.mask = mask;
+          T.bigmask = bmask;
           T.win = R.gm.x;
           T.bytes = (unsigned)tot * (HASVAL ? 32u : 16u);
+          T.nact = __popc(mask);
         }
         __syncwarp();
       };
@@ -1603,20 +1650,22 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
         issue_copies(0, rr & 1u);
         gm_ahead = group_rec(2);
       } else if (warp == 0) {
-        ps.pcta[lane] = 0.0;
+        ps.pcta[0][lane] = 0.0;
+        ps.pcta[1][lane] = 0.0;
       }
       __syncthreads();
 
       bool done = false;
       int t = 0, r = 0;
 #ifdef SLIM_PROFILE_ROUNDS
-      long long prof[5] = {0, 0, 0, 0, 0};
+      long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       long long tick_ = clock64();
 #endif
       for (; t < maxit && !done; t++) {
         double dltx = 0.0;
         for (int g = 0; g < ng; g++, r++, rr++) {
           const unsigned buf = rr & 1u;
+          const unsigned xb = xr & 1u;  // exchange buffer of the round
           const RoundTab &T = ps.tab[r % 3];
           const unsigned mask = T.mask;
           double xi = 0.0;
@@ -1631,74 +1680,69 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
 
           // gather: staged small columns from shared memory, one consumer warp each; the rest from global
           {
-            // slots of this warp: the ord-th small column goes to consumer warp ord % NCW
-            int myb0 = -1, myb1 = -1, myb2 = -1;
-            {
-              int ord = 0;
-              for (unsigned mm = mask; mm; mm &= mm - 1) {
-                const int b = __ffs(mm) - 1;
-                if (T.s1[b] - T.s0[b] <= kSmallCol) {
-                  if (ord == warp) myb0 = b;
-                  else if (ord == warp + NCW) myb1 = b;
-                  else if (ord == warp + 2 * NCW) myb2 = b;
-                  ord++;
-                }
-              }
-            }
-            if (warp < NCW && myb0 >= 0) {
-              // fast path: every column of this warp is staged with at most one 16-byte chunk per lane --
-              // all yhat gathers (L2 latency) are issued before the first reduction
-              auto one_chunk = [&](int b) {
-                return b < 0 || (T.soff[b] >= 0 && ((T.s1[b] + 3) >> 2) - (T.s0[b] >> 2) <= 32) || T.s1[b] <= T.s0[b];
-              };
-              if (one_chunk(myb0) && one_chunk(myb1) && one_chunk(myb2)) {
-                double p0 = 0.0, p1 = 0.0, p2 = 0.0;
-                auto part_of = [&](int b) {
-                  double v = 0.0;
-                  if (b >= 0 && T.s1[b] > T.s0[b]) {
-                    const int s0 = T.s0[b], s1 = T.s1[b], ch0 = s0 >> 2, nch = ((s1 + 3) >> 2) - ch0;
-                    if (lane < nch) {
-                      Chunk c;
-                      c.ix = ps.sidx[buf][T.soff[b] + lane];
-                      if (HASVAL) c.vv = ps.sval[HASVAL ? buf : 0][HASVAL ? T.soff[b] + lane : 0];
-                      v = dot_chunk_r<HASVAL, true>(c, (ch0 + lane) * 4, s0, s1, yh);
-                    }
-                  }
-                  return v;
+            // slots of this warp (assigned by the producer when it built the table), three at a time
+            static_assert((kClusterNT / 32 - 1) * kWarpSlots >= 32, "not enough consumer warp slots");
+            SLIM_TICK(5);
+            if (warp < NCW) {
+              for (int g0 = 0; g0 < kWarpSlots; g0 += 3) {
+                const int myb0 = T.wslot[warp][g0];
+                const int myb1 = g0 + 1 < kWarpSlots ? T.wslot[warp][g0 + 1] : -1;
+                const int myb2 = g0 + 2 < kWarpSlots ? T.wslot[warp][g0 + 2] : -1;
+                if (myb0 < 0) break;
+                // fast path: every column is staged with at most one 16-byte chunk per lane -- all yhat
+                // gathers (L2 latency) are issued before the first reduction
+                auto one_chunk = [&](int b) {
+                  return b < 0 || (T.soff[b] >= 0 && ((T.s1[b] + 3) >> 2) - (T.s0[b] >> 2) <= 32) || T.s1[b] <= T.s0[b];
                 };
-                p0 = part_of(myb0);
-                p1 = part_of(myb1);
-                p2 = part_of(myb2);
+                if (one_chunk(myb0) && one_chunk(myb1) && one_chunk(myb2)) {
+                  auto part_of = [&](int b) {
+                    double v = 0.0;
+                    if (b >= 0 && T.s1[b] > T.s0[b]) {
+                      const int s0 = T.s0[b], s1 = T.s1[b], ch0 = s0 >> 2, nch = ((s1 + 3) >> 2) - ch0;
+                      if (lane < nch) {
+                        Chunk c;
+                        c.ix = ps.sidx[buf][T.soff[b] + lane];
+                        if (HASVAL) c.vv = ps.sval[HASVAL ? buf : 0][HASVAL ? T.soff[b] + lane : 0];
+                        v = dot_chunk_r<HASVAL, true>(c, (ch0 + lane) * 4, s0, s1, yh);
+                      }
+                    }
+                    return v;
+                  };
+                  double p0 = part_of(myb0);
+                  double p1 = part_of(myb1);
+                  double p2 = part_of(myb2);
 #pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                  p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-                  p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-                  p2 += __shfl_xor_sync(0xffffffffu, p2, o);
-                }
-                if (lane == 0) {
-                  ps.pcta[myb0] = p0;
-                  if (myb1 >= 0) ps.pcta[myb1] = p1;
-                  if (myb2 >= 0) ps.pcta[myb2] = p2;
-                }
-              } else {
-                const int mine[3] = {myb0, myb1, myb2};
+                  for (int o = 16; o; o >>= 1) {
+                    p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+                    p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                    p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+                  }
+                  if (lane == 0) {
+                    ps.pcta[xb][myb0] = p0;
+                    if (myb1 >= 0) ps.pcta[xb][myb1] = p1;
+                    if (myb2 >= 0) ps.pcta[xb][myb2] = p2;
+                  }
+                } else {
+                  const int mine[3] = {myb0, myb1, myb2};
 #pragma unroll
-                for (int k = 0; k < 3; k++) {
-                  const int b = mine[k];
-                  if (b < 0) continue;
-                  const int s0 = T.s0[b], s1 = T.s1[b];
-                  if (s1 <= s0) continue;
-                  const int so = T.soff[b];
-                  const double v = so >= 0 ? warp_dot_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, yh)
-                                           : warp_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
-                  if (lane == 0) ps.pcta[b] = v;
+                  for (int k = 0; k < 3; k++) {
+                    const int b = mine[k];
+                    if (b < 0) continue;
+                    const int s0 = T.s0[b], s1 = T.s1[b];
+                    if (s1 <= s0) continue;
+                    const int so = T.soff[b];
+                    const double v = so >= 0 ? warp_dot_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, yh)
+                                             : warp_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
+                    if (lane == 0) ps.pcta[xb][b] = v;
+                  }
                 }
               }
             }
-            for (unsigned mm = mask; mm; mm &= mm - 1) {
+            SLIM_TICK(6);
+            for (unsigned mm = T.bigmask; mm; mm &= mm - 1) {
               const int b = __ffs(mm) - 1;
               const int s0 = T.s0[b], s1 = T.s1[b];
-              if (s1 - s0 > kSmallCol) {
+              {
                 double v = block_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1708,44 +1752,73 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
                   double sum = 0.0;
 #pragma unroll
                   for (int i = 0; i < NW; i++) sum += ps.pw[i];
-                  ps.pcta[b] = sum;
+                  ps.pcta[xb][b] = sum;
                 }
                 __syncthreads();
               }
             }
           }
+          SLIM_TICK(7);
           __syncthreads();
           SLIM_TICK(1);
           {
-            const int dst = tid >> 5, b = tid & 31;
-            if (dst < cs) *cl.map_shared_rank(&ps.pall[par][rank][b], dst) = ps.pcta[b];
+            // all-gather of the 32 partials across the cluster: every CTA bulk-copies its 256 bytes into
+            // every CTA's pall[xb][rank][.]; the receiver's mbarrier counts the bytes
+            if (tid == 0) mbar_expect_tx(&ps.xbar[xb], (uint32_t)cs * 256u);
+            if (tid < cs) {  // one 256-byte message per destination CTA
+              fence_proxy_async();  // pcta was written with ordinary stores
+              bulk_s2peer(&ps.pall[xb][rank][0], &ps.pcta[xb][0], 256u, &ps.xbar[xb], (uint32_t)tid);
+            }
           }
-          cl.sync();
+          SLIM_TICK(8);
           SLIM_TICK(2);
 
           // Gram-space sequential solve of the window by warp 0 (identical in every CTA)
           if (warp == 0) {
             const bool act = (mask >> lane) & 1u;
-            double P = 0.0;
-            if (act)
-              for (int c = 0; c < cs; c++) P += ps.pall[par][c][lane];
-            const double in_old = fabs(xi) > kEps ? xi : 0.0;
             const double aty = act ? (double)T.aty[lane] : 0.0;
             const double inv_den = act ? T.inv_den[lane] : 0.0;
-            double ip = P - in_old * (act ? T.sq[lane] : 0.0);
+            const double sqv = act ? T.sq[lane] : 0.0;
+            const int nact = T.nact;
+            int mb = T.abit[0];
+            double grow = ps.G[buf][mb][lane];
+            mbar_wait(&ps.xbar[xb], (xr >> 1) & 1u);  // the partials of all CTAs have landed
+            // the other buffer's outgoing copies (previous round) were consumed by every peer before it could
+            // contribute to this round: safe to clear it for the next round
+            ps.pcta[xb ^ 1u][lane] = 0.0;
+            double P = 0.0;
+            if (act)
+              for (int c = 0; c < cs; c++) P += ps.pall[xb][c][lane];
+            const double in_old = fabs(xi) > kEps ? xi : 0.0;
+            // With d_m = in_new_m - in_old_m the sequential inner product of slot k is
+            //   ip_k = P_k - in_old_k*sq_k - sum_{m<k} in_old_m G[m][k] + sum_{m<k} in_new_m G[m][k].
+            // The in_old sum does not depend on the chain: every lane accumulates it up front (throughput
+            // bound); the dependent chain per slot is then DADD -> SHFL -> select -> DFMA.
+            double ip = P - in_old * sqv;
+            for (int k = 0; k < nact; k++) {
+              const int m = T.abit[k];
+              const double o = __shfl_sync(0xffffffffu, in_old, m);
+              if (m < lane) ip = fma(-o, ps.G[buf][m][lane], ip);
+            }
+            const double cthr = aty - a.l1r;      // x' = max(cthr - ip, 0) * inv_den
+            const double den = act ? 1.0 / inv_den : 1.0;
+            const double qeps = kEps * den;       // |x'| > EPS  <=>  q > EPS * den   (q >= 0)
             double nx = xi, d = 0.0;
-            for (unsigned mm = mask; mm; mm &= mm - 1) {
-              const int mb = __ffs(mm) - 1;
-              double dm = 0.0;
+            for (int k = 0; k < nact; k++) {
+              const int mb_next = T.abit[k + 1 < nact ? k + 1 : k];
+              const double grow_next = ps.G[buf][mb_next][lane];
+              // slot mb: q = numerator of the update; broadcast q*inv_den when it enters yhat, else 0
+              const double q = cthr - ip;
+              const double xq = q > 0.0 ? q * inv_den : 0.0;
+              const double inn = q > qeps ? xq : 0.0;
+              const double in_new_b = __shfl_sync(0xffffffffu, inn, mb);
               if (lane == mb) {
-                const double num = aty - ip;
-                nx = num > a.l1r ? (num - a.l1r) * inv_den : 0.0;
-                const double in_new = fabs(nx) > kEps ? nx : 0.0;
-                d = in_new - in_old;
-                dm = d;
+                nx = xq;
+                d = inn - in_old;
               }
-              dm = __shfl_sync(0xffffffffu, dm, mb);
-              if (dm != 0.0 && act && lane > mb) ip += dm * ps.G[buf][mb][lane];
+              ip = fma(in_new_b, grow, ip);  // only later slots still use ip; the diagonal of G is zero
+              mb = mb_next;
+              grow = grow_next;
             }
             if (act) x[T.p[lane]] = nx;
             ps.dlt[lane] = act ? d : 0.0;
@@ -1753,36 +1826,37 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
 #pragma unroll
             for (int o = 16; o; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
             if (lane == 0) ps.dl = dd;
-          } else if (warp == 1) {
-            ps.pcta[lane] = 0.0;  // every CTA has read the partials (cluster barrier above): clear for the next round
+            SLIM_TICK(9);
           }
           __syncthreads();
           SLIM_TICK(3);
           dltx += ps.dl;
 
           // update this CTA's yhat slice: yhat += sum_k d_k a_k  (fp64 atomics: columns may share users)
-          {
-            int ord = 0;
-            for (unsigned mm = mask; mm; mm &= mm - 1) {
-              const int b = __ffs(mm) - 1;
-              const int s0 = T.s0[b], s1 = T.s1[b];
+          if (warp < NCW) {
+#pragma unroll
+            for (int k = 0; k < kWarpSlots; k++) {
+              const int b = T.wslot[warp][k];
+              if (b < 0) break;
               const double d = ps.dlt[b];
-              if (s1 - s0 <= kSmallCol) {
-                if ((ord == warp || ord == warp + NCW || ord == warp + 2 * NCW) && warp < NCW && d != 0.0 && s1 > s0) {
-                  const int so = T.soff[b];
-                  if (so >= 0) warp_axpy_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, d, yh);
-                  else warp_axpy<HASVAL>(a, T.c0[b], s0, s1, d, yh);
-                }
-                ord++;
-              } else if (d != 0.0) {
-                block_axpy<HASVAL>(a, T.c0[b], s0, s1, d, yh);
+              const int s0 = T.s0[b], s1 = T.s1[b];
+              if (d != 0.0 && s1 > s0) {
+                const int so = T.soff[b];
+                if (so >= 0) warp_axpy_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, d, yh);
+                else warp_axpy<HASVAL>(a, T.c0[b], s0, s1, d, yh);
               }
             }
           }
+          for (unsigned mm = T.bigmask; mm; mm &= mm - 1) {
+            const int b = __ffs(mm) - 1;
+            const double d = ps.dlt[b];
+            if (d != 0.0) block_axpy<HASVAL>(a, T.c0[b], T.s0[b], T.s1[b], d, yh);
+          }
+          SLIM_TICK(10);
           if (warp == NW - 1) tab_store(r + 2, treg);  // ... consumed here, a whole round later
           __syncthreads();
           SLIM_TICK(4);
-          par ^= 1;
+          xr++;
         }
         if (dltx < a.opttol) done = true;
       }
@@ -1792,9 +1866,14 @@ __global__ void __launch_bounds__(kClusterNT, 1) cd_cluster_kernel(const SolveAr
       rr++;
       __syncthreads();
 #ifdef SLIM_PROFILE_ROUNDS
-      if (rank == 0 && tid == 0)
-        printf("target %d na %d ng %d sweeps %d cycles: meta %lld gather %lld exchange %lld solve %lld update %lld\n",
-               j, na, ng, t, prof[0], prof[1], prof[2], prof[3], prof[4]);
+      if (rank == 0 && (tid == 0 || tid == 32 * (NW - 1))) {
+        const double rnds = (double)ng * t;
+        printf("target %d %s na %d ng %d sw %d | wait %.0f scan %.0f dots %.0f bigloop %.0f sync1 %.0f dsmem %.0f clbar %.0f "
+               "solve %.0f sync3 %.0f upd %.0f sync4 %.0f\n",
+               j, tid == 0 ? "C" : "P", na, ng, t, prof[0] / rnds, prof[5] / rnds, prof[6] / rnds, prof[7] / rnds,
+               prof[1] / rnds, prof[8] / rnds, prof[2] / rnds, prof[9] / rnds, prof[3] / rnds, prof[10] / rnds,
+               prof[4] / rnds);
+      }
 #endif
     } else if (na > 0 && maxit > 0) {
       CoordView v_cur = load_view(&meta[0], pr0, pr1);
