@@ -58,10 +58,10 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SLIM_BENCH_WORKLOAD", "c4"))
-    ap.add_argument("--cols-per-step", type=int, default=int(os.environ.get("SLIM_BENCH_COLS", "296")),
+    ap.add_argument("--cols-per-step", type=int, default=int(os.environ.get("SLIM_BENCH_COLS", "592")),
                     help="target columns per step PER GPU")
     ap.add_argument("--cpu-cols", type=int, default=int(os.environ.get("SLIM_BENCH_CPU_COLS", "0")),
-                    help="columns per reference step (0: one per host thread)")
+                    help="columns per reference step (0: four per host thread)")
     ap.add_argument("--l1r", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -199,7 +199,7 @@ def run_reference(args, rp, ri, rv, colcnt, steps, warmup):
     from slim_b200.synth import stratified_columns
 
     nthreads = os.cpu_count() or 1
-    ncs = args.cpu_cols or nthreads
+    ncs = args.cpu_cols or 4 * nthreads
     times, walls = [], []
     for s in range(warmup + steps):
         cols = stratified_columns(colcnt, ncs, offset=s)
