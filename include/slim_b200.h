@@ -42,8 +42,11 @@ int32_t SLIMB200_MatrixInfo(const slimb200_matrix_t *matrix, int32_t *nrows, int
 int32_t SLIMB200_MatrixCSC(const slimb200_matrix_t *matrix, int64_t *colptr, int32_t *colind,
                            float *colval, float *cnorms);
 
+/* The engine relabels items by popularity internally (internal id = position when items are sorted by
+ * descending nnz, ties by ascending id); rank[original id] = internal id.  Results always use original ids. */
+int32_t SLIMB200_MatrixItemOrder(const slimb200_matrix_t *matrix, int32_t *rank);
 /* Copy the staged window Gram blocks back (tests): double[ceil(ncols/32)][32][32], block w holds
- * <a_k, a_m> for the item columns 32w+k and 32w+m (zero diagonal). */
+ * <a_k, a_m> for the items with INTERNAL ids 32w+k and 32w+m (zero diagonal). */
 int32_t SLIMB200_MatrixWindowGram(const slimb200_matrix_t *matrix, double *out);
 
 /* Solve target columns cols[0..ncols_sel) (cols == NULL: every column): the per-column body of

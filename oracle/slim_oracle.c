@@ -140,6 +140,8 @@ static void shuffle_ref(act_t *list, int32_t n) {
 typedef struct {
   double *x, *aty, *y, *yhat, *csq;
   act_t *act;
+  const int32_t *rank; /* ORACLE_ORDER_POPULARITY: position of every item in the visiting order */
+  act_t *tmp;
 } work_t;
 
 static int32_t solve_column(const oracle_csc_t *m, const oracle_params_t *p, int32_t jc,
@@ -172,6 +174,28 @@ static int32_t solve_column(const oracle_csc_t *m, const oracle_params_t *p, int
       w->x[i] = -0.1; /* estimate.c:440 flag */
       actnnz += m->colptr[i + 1] - m->colptr[i];
     }
+  }
+
+  /* ORACLE_ORDER_POPULARITY: reorder the active list once (the order is free, cd.c shuffles it) */
+  if (p->order == ORACLE_ORDER_POPULARITY && na > 1) {
+    /* counting placement by rank: ranks are distinct, so a sort by rank via a dense scatter */
+    int32_t q = 0;
+    for (i = 0; i < na; i++) w->tmp[i] = w->act[i];
+    /* simple insertion into rank order: na is small compared with ncols; use qsort-free merge */
+    {
+      int32_t a, b;
+      for (a = 1; a < na; a++) {
+        act_t key = w->tmp[a];
+        b = a - 1;
+        while (b >= 0 && w->rank[w->tmp[b].val] > w->rank[key.val]) {
+          w->tmp[b + 1] = w->tmp[b];
+          b--;
+        }
+        w->tmp[b + 1] = key;
+      }
+    }
+    for (i = 0; i < na; i++) w->act[i] = w->tmp[i];
+    (void)q;
   }
 
   /* estimate.c:448-449 */
@@ -278,6 +302,7 @@ int oracle_learn(const oracle_csc_t *m, const oracle_params_t *p, const int32_t 
   double *csq;
   int64_t *rowlen = NULL;
   int64_t tot;
+  int32_t *rank = NULL;
 
   if (cols == NULL) nsel = ncols;
   if (p->order == ORACLE_ORDER_REF_RAND) nthreads = 1;
@@ -296,6 +321,20 @@ int oracle_learn(const oracle_csc_t *m, const oracle_params_t *p, const int32_t 
     else
       a = (double)(m->colptr[s + 1] - m->colptr[s]);
     csq[s] = a;
+  }
+  if (p->order == ORACLE_ORDER_POPULARITY) {
+    /* rank[i] = position of item i when items are sorted by (descending nnz, ascending id):
+       counting sort over the column lengths, stable in the id */
+    int64_t maxc = 0, *start;
+    int32_t i;
+    for (i = 0; i < ncols; i++)
+      if (m->colptr[i + 1] - m->colptr[i] > maxc) maxc = m->colptr[i + 1] - m->colptr[i];
+    start = (int64_t *)calloc((size_t)maxc + 2, sizeof(int64_t));
+    for (i = 0; i < ncols; i++) start[maxc - (m->colptr[i + 1] - m->colptr[i]) + 1]++;
+    for (i = 0; i <= maxc; i++) start[i + 1] += start[i];
+    rank = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ncols > 0 ? ncols : 1));
+    for (i = 0; i < ncols; i++) rank[i] = (int32_t)start[maxc - (m->colptr[i + 1] - m->colptr[i])]++;
+    free(start);
   }
   if (stats && stats->expand_nnz) {
     int64_t k;
@@ -316,7 +355,9 @@ int oracle_learn(const oracle_csc_t *m, const oracle_params_t *p, const int32_t 
     w.y = (double *)calloc((size_t)(nrows > 0 ? nrows : 1), sizeof(double));
     w.yhat = (double *)calloc((size_t)(nrows > 0 ? nrows : 1), sizeof(double));
     w.act = (act_t *)malloc(sizeof(act_t) * (size_t)(ncols > 0 ? ncols : 1));
+    w.tmp = (act_t *)malloc(sizeof(act_t) * (size_t)(ncols > 0 ? ncols : 1));
     w.csq = csq;
+    w.rank = rank;
 
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 1)
@@ -350,6 +391,7 @@ int oracle_learn(const oracle_csc_t *m, const oracle_params_t *p, const int32_t 
     free(w.y);
     free(w.yhat);
     free(w.act);
+    free(w.tmp);
     free(tind);
     free(tval);
   }
@@ -372,6 +414,7 @@ int oracle_learn(const oracle_csc_t *m, const oracle_params_t *p, const int32_t 
   free(lnnz);
   free(csq);
   free(rowlen);
+  free(rank);
   return 0;
 }
 

@@ -333,6 +333,12 @@ class Staged:
         assert rc == SLIM_OK
         return dict(colptr=cp, colind=ci[:self.nnz], colval=cv[:self.nnz], cnorms=cn[:self.ncols])
 
+    def item_order(self):
+        """rank[original item id] = internal (popularity-ordered) id."""
+        rank = np.zeros(max(self.ncols, 1), np.int32)
+        assert self._lib.SLIMB200_MatrixItemOrder(self.handle, _ptr(rank, C.c_int32)) == SLIM_OK
+        return rank[:self.ncols]
+
     def window_gram(self):
         nwin = (self.ncols + 31) // 32
         out = np.zeros((max(nwin, 1), 32, 32), np.float64)

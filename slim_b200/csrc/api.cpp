@@ -736,6 +736,11 @@ int32_t SLIMB200_MatrixCSC(const slimb200_matrix_t *matrix, int64_t *colptr, int
   return matrix_csc_to_host(reinterpret_cast<const Matrix *>(matrix), colptr, colind, colval, cnorms);
 }
 
+int32_t SLIMB200_MatrixItemOrder(const slimb200_matrix_t *matrix, int32_t *rank) {
+  if (!matrix) return SLIM_ERROR_INPUT;
+  return matrix_item_order_to_host(reinterpret_cast<const Matrix *>(matrix), rank);
+}
+
 int32_t SLIMB200_MatrixWindowGram(const slimb200_matrix_t *matrix, double *out) {
   if (!matrix) return SLIM_ERROR_INPUT;
   return matrix_window_gram_to_host(reinterpret_cast<const Matrix *>(matrix), out);

@@ -30,6 +30,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 
 namespace cg = cooperative_groups;
 
@@ -111,6 +112,13 @@ struct Matrix {
   bool has_val = false;   // the caller passed a value array
   bool unit = false;      // ... and every stored value is exactly 1.0f: the kernels then skip the value
                           // stream (4 B per nonzero instead of 8), same arithmetic as the binary path
+  // Items are RELABELED by popularity inside the engine: internal id = position of the item when items
+  // are sorted by (descending nnz, ascending id).  A target's active items are mostly popular ones, so
+  // in this order they fall into few, densely filled 32-item windows (see cd_cluster_kernel).  Every
+  // device structure below uses internal ids; results are mapped back before they leave the engine.
+  int32_t *d_rank = nullptr;      // original id -> internal id
+  int32_t *d_inv = nullptr;       // internal id -> original id
+  std::vector<int32_t> h_rank, h_inv;
   double *d_wgram = nullptr;      // [ceil(ncols/32)][32][32] Gram blocks of 32 consecutive item columns
   int32_t rows_per_part = 0;      // user-range width of the 16-way column split (cluster kernel)
   int32_t *d_colsplit = nullptr;  // [ncols][kParts+1] entry offsets of the user ranges in each column
@@ -148,6 +156,8 @@ void free_matrix(Matrix *m) {
   cudaFree(m->d_csq);
   cudaFree(m->d_colsplit);
   cudaFree(m->d_wgram);
+  cudaFree(m->d_rank);
+  cudaFree(m->d_inv);
   cudaFree(m->d_scratch);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -193,6 +203,12 @@ __global__ void count_columns_kernel(const int32_t *__restrict__ ind, int64_t n,
     atomicAdd(&cnt[ind[k]], 1);
     pos[k] = (uint32_t)k;
   }
+}
+
+__global__ void relabel_items_kernel(int32_t *ind, int64_t n, const int32_t *__restrict__ rank) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x)
+    ind[k] = rank[ind[k]];
 }
 
 // Single-CTA scan over the column counts: colptr (padded to 4 entries) and cstart (unpadded).
@@ -472,6 +488,33 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
                                                                           m->d_colcnt, d_pos.p);
       m->stage_launches++;
     }
+    // popularity relabeling: internal id = rank by (descending nnz, ascending id)
+    {
+      std::vector<int32_t> cnt0(ncols);
+      if (ncols > 0)
+        CK(cudaMemcpyAsync(cnt0.data(), m->d_colcnt, sizeof(int32_t) * ncols, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      m->h_inv.resize(ncols);
+      m->h_rank.resize(ncols);
+      std::iota(m->h_inv.begin(), m->h_inv.end(), 0);
+      const bool relabel = !(getenv("SLIMB200_NO_RELABEL") && atoi(getenv("SLIMB200_NO_RELABEL")));
+      if (relabel)
+        std::stable_sort(m->h_inv.begin(), m->h_inv.end(), [&](int32_t x, int32_t y) { return cnt0[x] > cnt0[y]; });
+      for (int32_t n = 0; n < ncols; n++) m->h_rank[m->h_inv[n]] = n;
+      CK(cudaMalloc(&m->d_rank, sizeof(int32_t) * std::max<int32_t>(ncols, 1)));
+      CK(cudaMalloc(&m->d_inv, sizeof(int32_t) * std::max<int32_t>(ncols, 1)));
+      if (ncols > 0) {
+        CK(cudaMemcpyAsync(m->d_rank, m->h_rank.data(), sizeof(int32_t) * ncols, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(m->d_inv, m->h_inv.data(), sizeof(int32_t) * ncols, cudaMemcpyHostToDevice, s));
+      }
+      if (nnz > 0 && relabel) {
+        relabel_items_kernel<<<grid_for(nnz, 256, m->sm_count), 256, 0, s>>>(m->d_rowind, nnz, m->d_rank);
+        CK(cudaMemsetAsync(m->d_colcnt, 0, sizeof(int32_t) * ncols, s));
+        count_columns_kernel<<<grid_for(nnz, 256, m->sm_count), 256, 0, s>>>(m->d_rowind, nnz, m->d_colcnt, d_pos.p);
+        m->stage_launches += 2;
+        CK(cudaStreamSynchronize(s));  // h_rank / h_inv staging buffers are read by the copies above
+      }
+    }
     scan_columns_kernel<<<1, 1024, 0, s>>>(m->d_colcnt, ncols, m->d_colptr, d_cstart.p);
     m->stage_launches++;
     m->h_colcnt.resize(ncols);
@@ -588,6 +631,11 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
   return nullptr;
 }
 
+int matrix_item_order_to_host(const Matrix *m, int32_t *rank) {
+  if (m->ncols > 0) memcpy(rank, m->h_rank.data(), sizeof(int32_t) * m->ncols);
+  return kOk;
+}
+
 int matrix_window_gram_to_host(const Matrix *m, double *out) {
   try {
     DeviceGuard guard(m->device);
@@ -616,16 +664,20 @@ int matrix_csc_to_host(const Matrix *m, int64_t *colptr, int32_t *colind, float 
         CK(cudaMemcpy(pval.data(), m->d_colval, sizeof(float) * m->nnzp, cudaMemcpyDeviceToHost));
     }
     int64_t o = 0;
-    for (int32_t c = 0; c < m->ncols; c++) {
+    for (int32_t c = 0; c < m->ncols; c++) {  // c: ORIGINAL item id, n: internal id
+      const int32_t n = m->h_rank[c];
       colptr[c] = o;
-      for (int32_t e = 0; e < m->h_colcnt[c]; e++, o++) {
-        colind[o] = pind[pp[c] + e];
-        if (m->has_val && colval) colval[o] = pval[pp[c] + e];
+      for (int32_t e = 0; e < m->h_colcnt[n]; e++, o++) {
+        colind[o] = pind[pp[n] + e];
+        if (m->has_val && colval) colval[o] = pval[pp[n] + e];
       }
     }
     colptr[m->ncols] = o;
-    if (cnorms && m->ncols > 0)
-      CK(cudaMemcpy(cnorms, m->d_cnorms, sizeof(float) * m->ncols, cudaMemcpyDeviceToHost));
+    if (cnorms && m->ncols > 0) {
+      std::vector<float> cn(m->ncols);
+      CK(cudaMemcpy(cn.data(), m->d_cnorms, sizeof(float) * m->ncols, cudaMemcpyDeviceToHost));
+      for (int32_t c = 0; c < m->ncols; c++) cnorms[c] = cn[m->h_rank[c]];
+    }
     return kOk;
   } catch (const EngineError &e) {
     g_last_error = e.what();
@@ -655,9 +707,11 @@ struct SolveArgs {
   const float *colval;
   const float *cnorms;
   const double *csq;
+  const int32_t *rank;  // original item id -> internal id
+  const int32_t *inv;   // internal item id -> original id
   double l1r, l2r, opttol;
   int32_t maxniters;
-  const int32_t *targets;
+  const int32_t *targets;  // internal ids
   int32_t ntargets;
   int32_t *queue;
   // warm start (CSC of the initial model), wcolptr == nullptr for cold start
@@ -821,11 +875,12 @@ __global__ void __launch_bounds__(NT) cd_solve_kernel(const SolveArgs a) {
       if (lane == 0) expand += (r1 - r0);
     }
     // warm start: scatter column j of the initial model (estimate.c:455-458)
-    const bool warm = a.wcolptr != nullptr && j < a.wncols;
+    const int jo = a.inv[j];  // original id of the target (the warm-start model is indexed by original ids)
+    const bool warm = a.wcolptr != nullptr && jo < a.wncols;
     if (warm) {
-      for (int64_t k = a.wcolptr[j] + tid; k < a.wcolptr[j + 1]; k += NT) {
+      for (int64_t k = a.wcolptr[jo] + tid; k < a.wcolptr[jo + 1]; k += NT) {
         const int r = a.wcolind[k];
-        if (r >= 0 && r < a.ncols) xw[r] = a.wcolval[k];
+        if (r >= 0 && r < a.ncols) xw[a.rank[r]] = a.wcolval[k];
       }
     }
     __threadfence_block();
@@ -861,9 +916,9 @@ __global__ void __launch_bounds__(NT) cd_solve_kernel(const SolveArgs a) {
     }
     team_sync<NT>();
     if (warm) {
-      for (int64_t k = a.wcolptr[j] + tid; k < a.wcolptr[j + 1]; k += NT) {
+      for (int64_t k = a.wcolptr[jo] + tid; k < a.wcolptr[jo + 1]; k += NT) {
         const int r = a.wcolind[k];
-        if (r >= 0 && r < a.ncols) xw[r] = 0.0f;
+        if (r >= 0 && r < a.ncols) xw[a.rank[r]] = 0.0f;
       }
     }
 
@@ -1008,7 +1063,7 @@ __global__ void __launch_bounds__(NT) cd_solve_kernel(const SolveArgs a) {
         int tot;
         const int pos = w0 + team_excl_scan<NT>(flag, sc, tot);
         if (flag) {
-          a.pool_idx[off + pos] = act_idx[p];
+          a.pool_idx[off + pos] = a.inv[act_idx[p]];  // original item id
           a.pool_val[off + pos] = (float)xv;
         }
         w0 += tot;
@@ -1098,13 +1153,19 @@ __device__ __forceinline__ CoordView load_view(const ActMetaC *m, int pr0, int p
 // plain loads and stores).
 template <bool HASVAL, bool L2 = false>
 __device__ __forceinline__ double dot_chunk_r(const Chunk &r, int e0, int lo, int hi, const double *yh) {
-  double s = 0.0;
+  // The four gathers are UNCONDITIONAL (every id of a padded column chunk is a valid user id; entries
+  // outside [lo, hi) belong to another CTA's range or are padding) so that they issue back to back and
+  // their latencies overlap; the range test only selects which values are summed.
 #define SLIM_YH(i) (L2 ? __ldcg(yh + (i)) : yh[(i)])
-  if (e0 + 0 >= lo && e0 + 0 < hi) s += HASVAL ? (double)r.vv.x * SLIM_YH(r.ix.x) : SLIM_YH(r.ix.x);
-  if (e0 + 1 >= lo && e0 + 1 < hi) s += HASVAL ? (double)r.vv.y * SLIM_YH(r.ix.y) : SLIM_YH(r.ix.y);
-  if (e0 + 2 >= lo && e0 + 2 < hi) s += HASVAL ? (double)r.vv.z * SLIM_YH(r.ix.z) : SLIM_YH(r.ix.z);
-  if (e0 + 3 >= lo && e0 + 3 < hi) s += HASVAL ? (double)r.vv.w * SLIM_YH(r.ix.w) : SLIM_YH(r.ix.w);
+  const double y0 = SLIM_YH(r.ix.x), y1 = SLIM_YH(r.ix.y), y2 = SLIM_YH(r.ix.z), y3 = SLIM_YH(r.ix.w);
 #undef SLIM_YH
+  const bool k0 = e0 + 0 >= lo && e0 + 0 < hi, k1 = e0 + 1 >= lo && e0 + 1 < hi;
+  const bool k2 = e0 + 2 >= lo && e0 + 2 < hi, k3 = e0 + 3 >= lo && e0 + 3 < hi;
+  double s = 0.0;
+  s += k0 ? (HASVAL ? (double)r.vv.x * y0 : y0) : 0.0;
+  s += k1 ? (HASVAL ? (double)r.vv.y * y1 : y1) : 0.0;
+  s += k2 ? (HASVAL ? (double)r.vv.z * y2 : y2) : 0.0;
+  s += k3 ? (HASVAL ? (double)r.vv.w * y3 : y3) : 0.0;
   return s;
 }
 
@@ -1129,7 +1190,7 @@ constexpr int kClusterNT = SLIM_CLUSTER_NT;                 // threads per CTA o
 constexpr int kClusterCtasPerSm = kClusterNT <= 256 ? 2 : 1;  // two co-resident CTAs interleave their rounds
 constexpr int kWarpSlots = 5;  // small columns of a round per consumer warp: ceil(32 / (kClusterNT/32 - 1))
 
-constexpr int kSmallCol = 4096;  // entries of a column inside one CTA's user range handled by ONE warp
+constexpr int kSmallCol = 1024;  // entries of a column inside one CTA's user range handled by ONE warp
 
 struct ClusterSmem {
   double red[2][kClusterNT / 32];  // per-warp partials (double buffered)
@@ -1168,7 +1229,7 @@ struct __align__(128) PipeSmem {
   uint4 sidx[2][CAP];                               // staged user ids of the round's small columns
   float4 sval[HASVAL ? 2 : 1][HASVAL ? CAP : 1];    // ... and their values
   double G[2][32][32];                              // Gram block of the window, G[m][k] = <a_m, a_k>
-  double pall[2][kParts][32];                       // partial inner products of every CTA (DSMEM exchange)
+  unsigned long long pall[2][kParts][32][2];        // partial inner products of every CTA: {lo32|tag}, {hi32|tag}
   RoundTab tab[3];
   double pcta[2][32];                               // this CTA's partial inner products per slot (per exchange buffer)
   double dlt[32];                                   // yhat step per slot
@@ -1224,6 +1285,47 @@ __device__ __forceinline__ void bulk_s2peer(void *local_dst, const void *local_s
                "r"(smem_u32(local_src)), "r"(bytes), "r"(rbar)
                : "memory");
 }
+// Flag-in-data exchange (the "LL" idea of NCCL): every 8-byte remote store carries 4 bytes of payload
+// and a 4-byte round tag; 8-byte stores are single-copy atomic, so the receiver simply polls its OWN
+// shared memory until all tags match -- no fence, no barrier, no mbarrier on the critical path.
+__device__ __forceinline__ void st_peer_tagged(unsigned long long *local_dst, uint32_t peer_rank, double v,
+                                               uint32_t tag) {
+  uint32_t rdst;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(local_dst)), "r"(peer_rank));
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)tag << 32);
+  const unsigned long long w1 = (bits >> 32) | ((unsigned long long)tag << 32);
+  asm volatile("st.shared::cluster.v2.u64 [%0], {%1, %2};" ::"r"(rdst), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double ld_tagged_wait(const unsigned long long *src, uint32_t tag) {
+  unsigned long long w0, w1;
+  const uint32_t addr = smem_u32(src);
+  do {
+    asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(addr) : "memory");
+  } while ((uint32_t)(w0 >> 32) != tag || (uint32_t)(w1 >> 32) != tag);
+  return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+// (kept for reference) generic-proxy exchange with a release-arrive on the PEER's mbarrier
+__device__ __forceinline__ void st_peer_f64(double *local_dst, uint32_t peer_rank, double v) {
+  uint32_t rdst;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(local_dst)), "r"(peer_rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(rdst), "d"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_peer(unsigned long long *local_bar, uint32_t peer_rank) {
+  uint32_t rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar)), "r"(peer_rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // <a, yhat> / yhat += d a over a STAGED column range: user ids (and values) come from shared memory
@@ -1233,8 +1335,26 @@ __device__ __forceinline__ double warp_dot_staged(const uint4 *sidx, const float
   const int lane = threadIdx.x & 31;
   const int ch0 = s0 >> 2, nch = ((s1 + 3) >> 2) - ch0;
   double part = 0.0;
-#pragma unroll 2
-  for (int k = lane; k < nch; k += 32) {
+  int k = lane;
+  for (; k + 96 < nch; k += 128) {  // 4 chunks = 16 yhat gathers in flight per lane
+    Chunk c0, c1, c2, c3;
+    c0.ix = sidx[k];
+    c1.ix = sidx[k + 32];
+    c2.ix = sidx[k + 64];
+    c3.ix = sidx[k + 96];
+    if (HASVAL) {
+      c0.vv = sval[k];
+      c1.vv = sval[k + 32];
+      c2.vv = sval[k + 64];
+      c3.vv = sval[k + 96];
+    }
+    const double a0 = dot_chunk_r<HASVAL, true>(c0, (ch0 + k) * 4, s0, s1, yh);
+    const double a1 = dot_chunk_r<HASVAL, true>(c1, (ch0 + k + 32) * 4, s0, s1, yh);
+    const double a2 = dot_chunk_r<HASVAL, true>(c2, (ch0 + k + 64) * 4, s0, s1, yh);
+    const double a3 = dot_chunk_r<HASVAL, true>(c3, (ch0 + k + 96) * 4, s0, s1, yh);
+    part += (a0 + a1) + (a2 + a3);
+  }
+  for (; k < nch; k += 32) {
     Chunk c;
     c.ix = sidx[k];
     if (HASVAL) c.vv = sval[k];
@@ -1397,11 +1517,12 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
   double *yh = a.yhat + (size_t)cid * a.row_stride;
 
   if (WINDOW) {
+    for (int k = tid; k < 2 * kParts * 32 * 2; k += NT) (&ps.pall[0][0][0][0])[k] = 0ull;  // tag 0 = "nothing yet"
     if (tid == 0) {
       mbar_init(&ps.mbar[0], 1);
       mbar_init(&ps.mbar[1], 1);
-      mbar_init(&ps.xbar[0], 1);
-      mbar_init(&ps.xbar[1], 1);
+      mbar_init(&ps.xbar[0], (uint32_t)cs);  // one arrival per source CTA of the cluster
+      mbar_init(&ps.xbar[1], (uint32_t)cs);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       fence_proxy_async();
     }
@@ -1435,11 +1556,12 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
       }
       if (lane == 0) expand += (r1 - r0);
     }
-    const bool warm = a.wcolptr != nullptr && j < a.wncols;
+    const int jo = a.inv[j];  // original id of the target (the warm-start model is indexed by original ids)
+    const bool warm = a.wcolptr != nullptr && jo < a.wncols;
     if (warm && rank == 0) {
-      for (int64_t k = a.wcolptr[j] + tid; k < a.wcolptr[j + 1]; k += NT) {
+      for (int64_t k = a.wcolptr[jo] + tid; k < a.wcolptr[jo + 1]; k += NT) {
         const int r = a.wcolind[k];
-        if (r >= 0 && r < a.ncols) xw[r] = a.wcolval[k];
+        if (r >= 0 && r < a.ncols) xw[a.rank[r]] = a.wcolval[k];
       }
     }
     __threadfence();
@@ -1511,9 +1633,9 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
     __syncthreads();
     cl.sync();  // all CTAs have read xw before CTA 0 clears it
     if (warm && rank == 0) {
-      for (int64_t k = a.wcolptr[j] + tid; k < a.wcolptr[j + 1]; k += NT) {
+      for (int64_t k = a.wcolptr[jo] + tid; k < a.wcolptr[jo + 1]; k += NT) {
         const int r = a.wcolind[k];
-        if (r >= 0 && r < a.ncols) xw[r] = 0.0f;
+        if (r >= 0 && r < a.ncols) xw[a.rank[r]] = 0.0f;
       }
     }
 
@@ -1625,7 +1747,6 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
       auto group_rec = [&](int r) { return __ldcg(reinterpret_cast<const int4 *>(groups + (r % ng))); };
       auto issue_copies = [&](int r, unsigned buf) {  // producer warp: stage local round r into buffer buf
         const RoundTab &T = ps.tab[r % 3];
-        fence_proxy_async();
         if (lane == 0) mbar_expect_tx(&ps.mbar[buf], T.bytes + 8192u);
         __syncwarp();
         if (((T.mask >> lane) & 1u) && T.soff[lane] >= 0) {
@@ -1671,7 +1792,6 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
           double xi = 0.0;
           if (warp == 0 && ((mask >> lane) & 1u)) xi = x[T.p[lane]];  // consumed by the solve
           if (warp == NW - 1) {
-            issue_copies(r + 1, buf ^ 1u);  // next round's columns + Gram block (tables are one round ahead)
             tab_load(gm_ahead, treg);       // start reading the coordinate lines of round r + 2 ...
             gm_ahead = group_rec(r + 3);    // ... and the window record of round r + 3
           }
@@ -1683,58 +1803,61 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
             // slots of this warp (assigned by the producer when it built the table), three at a time
             static_assert((kClusterNT / 32 - 1) * kWarpSlots >= 32, "not enough consumer warp slots");
             SLIM_TICK(5);
-            if (warp < NCW) {
-              for (int g0 = 0; g0 < kWarpSlots; g0 += 3) {
-                const int myb0 = T.wslot[warp][g0];
-                const int myb1 = g0 + 1 < kWarpSlots ? T.wslot[warp][g0 + 1] : -1;
-                const int myb2 = g0 + 2 < kWarpSlots ? T.wslot[warp][g0 + 2] : -1;
-                if (myb0 < 0) break;
-                // fast path: every column is staged with at most one 16-byte chunk per lane -- all yhat
-                // gathers (L2 latency) are issued before the first reduction
-                auto one_chunk = [&](int b) {
-                  return b < 0 || (T.soff[b] >= 0 && ((T.s1[b] + 3) >> 2) - (T.s0[b] >> 2) <= 32) || T.s1[b] <= T.s0[b];
-                };
-                if (one_chunk(myb0) && one_chunk(myb1) && one_chunk(myb2)) {
-                  auto part_of = [&](int b) {
-                    double v = 0.0;
-                    if (b >= 0 && T.s1[b] > T.s0[b]) {
-                      const int s0 = T.s0[b], s1 = T.s1[b], ch0 = s0 >> 2, nch = ((s1 + 3) >> 2) - ch0;
-                      if (lane < nch) {
-                        Chunk c;
-                        c.ix = ps.sidx[buf][T.soff[b] + lane];
-                        if (HASVAL) c.vv = ps.sval[HASVAL ? buf : 0][HASVAL ? T.soff[b] + lane : 0];
-                        v = dot_chunk_r<HASVAL, true>(c, (ch0 + lane) * 4, s0, s1, yh);
-                      }
+            if (warp < NCW && T.wslot[warp][0] >= 0) {
+              int myb[kWarpSlots];
+#pragma unroll
+              for (int k = 0; k < kWarpSlots; k++) myb[k] = T.wslot[warp][k];
+              // fast path: every column is staged with at most one 16-byte chunk per lane -- all yhat
+              // gathers (L2 latency) of all the warp's columns are issued before the first reduction
+              auto one_chunk = [&](int b) {
+                return b < 0 || (T.soff[b] >= 0 && ((T.s1[b] + 3) >> 2) - (T.s0[b] >> 2) <= 32) || T.s1[b] <= T.s0[b];
+              };
+              bool fast = true;
+#pragma unroll
+              for (int k = 0; k < kWarpSlots; k++) fast = fast && one_chunk(myb[k]);
+              SLIM_TICK(5);
+              if (fast) {
+                double pv[kWarpSlots];
+#pragma unroll
+                for (int k = 0; k < kWarpSlots; k++) {
+                  const int b = myb[k];
+                  double v = 0.0;
+                  if (b >= 0 && T.s1[b] > T.s0[b]) {
+                    const int s0 = T.s0[b], s1 = T.s1[b], ch0 = s0 >> 2, nch = ((s1 + 3) >> 2) - ch0;
+                    if (lane < nch) {
+                      Chunk c;
+                      c.ix = ps.sidx[buf][T.soff[b] + lane];
+                      if (HASVAL) c.vv = ps.sval[HASVAL ? buf : 0][HASVAL ? T.soff[b] + lane : 0];
+                      v = dot_chunk_r<HASVAL, true>(c, (ch0 + lane) * 4, s0, s1, yh);
                     }
-                    return v;
-                  };
-                  double p0 = part_of(myb0);
-                  double p1 = part_of(myb1);
-                  double p2 = part_of(myb2);
+                  }
+                  pv[k] = v;
+                }
+#ifdef SLIM_PROFILE_ROUNDS
+                if (pv[0] == 123.456) prof[11]++;  // force the gathers to complete before the tick
+#endif
+                SLIM_TICK(11);
 #pragma unroll
-                  for (int o = 16; o; o >>= 1) {
-                    p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-                    p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-                    p2 += __shfl_xor_sync(0xffffffffu, p2, o);
-                  }
-                  if (lane == 0) {
-                    ps.pcta[xb][myb0] = p0;
-                    if (myb1 >= 0) ps.pcta[xb][myb1] = p1;
-                    if (myb2 >= 0) ps.pcta[xb][myb2] = p2;
-                  }
-                } else {
-                  const int mine[3] = {myb0, myb1, myb2};
+                for (int o = 16; o; o >>= 1) {
 #pragma unroll
-                  for (int k = 0; k < 3; k++) {
-                    const int b = mine[k];
-                    if (b < 0) continue;
-                    const int s0 = T.s0[b], s1 = T.s1[b];
-                    if (s1 <= s0) continue;
-                    const int so = T.soff[b];
-                    const double v = so >= 0 ? warp_dot_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, yh)
-                                             : warp_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
-                    if (lane == 0) ps.pcta[xb][b] = v;
-                  }
+                  for (int k = 0; k < kWarpSlots; k++) pv[k] += __shfl_xor_sync(0xffffffffu, pv[k], o);
+                }
+                if (lane == 0) {
+#pragma unroll
+                  for (int k = 0; k < kWarpSlots; k++)
+                    if (myb[k] >= 0) ps.pcta[xb][myb[k]] = pv[k];
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < kWarpSlots; k++) {
+                  const int b = myb[k];
+                  if (b < 0) continue;
+                  const int s0 = T.s0[b], s1 = T.s1[b];
+                  if (s1 <= s0) continue;
+                  const int so = T.soff[b];
+                  const double v = so >= 0 ? warp_dot_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, yh)
+                                           : warp_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
+                  if (lane == 0) ps.pcta[xb][b] = v;
                 }
               }
             }
@@ -1761,17 +1884,17 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
           SLIM_TICK(7);
           __syncthreads();
           SLIM_TICK(1);
+          // next round's columns + Gram block (tables are one round ahead).  Issued AFTER the barrier: a CTA
+          // barrier waits for the CTA's bulk copies in flight, so they are given the exchange + solve phase
+          // to land instead of stalling the barrier above.
+          if (warp == NW - 1) issue_copies(r + 1, buf ^ 1u);
           {
-            // all-gather of the 32 partials across the cluster: every CTA bulk-copies its 256 bytes into
-            // every CTA's pall[xb][rank][.]; the receiver's mbarrier counts the bytes
-            if (tid == 0) mbar_expect_tx(&ps.xbar[xb], (uint32_t)cs * 256u);
-            if (tid < cs) {  // one 256-byte message per destination CTA
-              fence_proxy_async();  // pcta was written with ordinary stores
-              bulk_s2peer(&ps.pall[xb][rank][0], &ps.pcta[xb][0], 256u, &ps.xbar[xb], (uint32_t)tid);
-            }
+            // all-gather of the 32 partials across the cluster: warp w stores this CTA's 32 values, each
+            // tagged with the round number, into CTA w's pall[xb][rank][.] (coalesced DSMEM stores)
+            for (int dst = warp; dst < cs; dst += NW)
+              st_peer_tagged(&ps.pall[xb][rank][lane][0], (uint32_t)dst, ps.pcta[xb][lane], xr + 1u);
           }
           SLIM_TICK(8);
-          SLIM_TICK(2);
 
           // Gram-space sequential solve of the window by warp 0 (identical in every CTA)
           if (warp == 0) {
@@ -1782,13 +1905,13 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
             const int nact = T.nact;
             int mb = T.abit[0];
             double grow = ps.G[buf][mb][lane];
-            mbar_wait(&ps.xbar[xb], (xr >> 1) & 1u);  // the partials of all CTAs have landed
-            // the other buffer's outgoing copies (previous round) were consumed by every peer before it could
-            // contribute to this round: safe to clear it for the next round
-            ps.pcta[xb ^ 1u][lane] = 0.0;
-            double P = 0.0;
-            if (act)
-              for (int c = 0; c < cs; c++) P += ps.pall[xb][c][lane];
+            ps.pcta[xb ^ 1u][lane] = 0.0;  // clear the other buffer for the next round
+            double P = 0.0;  // poll until the tagged partials of all CTAs have landed (fixed summation order)
+            for (int c = 0; c < cs; c++) P += ld_tagged_wait(&ps.pall[xb][c][lane][0], xr + 1u);
+#ifdef SLIM_PROFILE_ROUNDS
+            if (P == 123.456) prof[2]++;
+#endif
+            SLIM_TICK(2);
             const double in_old = fabs(xi) > kEps ? xi : 0.0;
             // With d_m = in_new_m - in_old_m the sequential inner product of slot k is
             //   ip_k = P_k - in_old_k*sq_k - sum_{m<k} in_old_m G[m][k] + sum_{m<k} in_new_m G[m][k].
@@ -1868,9 +1991,9 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
 #ifdef SLIM_PROFILE_ROUNDS
       if (rank == 0 && (tid == 0 || tid == 32 * (NW - 1))) {
         const double rnds = (double)ng * t;
-        printf("target %d %s na %d ng %d sw %d | wait %.0f scan %.0f dots %.0f bigloop %.0f sync1 %.0f dsmem %.0f clbar %.0f "
-               "solve %.0f sync3 %.0f upd %.0f sync4 %.0f\n",
-               j, tid == 0 ? "C" : "P", na, ng, t, prof[0] / rnds, prof[5] / rnds, prof[6] / rnds, prof[7] / rnds,
+        printf("target %d %s na %d ng %d sw %d | wait %.0f setup %.0f gathers %.0f reduce %.0f bigloop %.0f sync1 %.0f xsend %.0f poll %.0f "
+               "chain %.0f sync3 %.0f upd %.0f sync4 %.0f\n",
+               j, tid == 0 ? "C" : "P", na, ng, t, prof[0] / rnds, prof[5] / rnds, prof[11] / rnds, prof[6] / rnds, prof[7] / rnds,
                prof[1] / rnds, prof[8] / rnds, prof[2] / rnds, prof[9] / rnds, prof[3] / rnds, prof[10] / rnds,
                prof[4] / rnds);
       }
@@ -2025,7 +2148,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
           int tot;
           const int pos = w0 + team_excl_scan<NT>(flag, sm.sc, tot);
           if (flag) {
-            a.pool_idx[off + pos] = act_idx[p];
+            a.pool_idx[off + pos] = a.inv[act_idx[p]];  // original item id
             a.pool_val[off + pos] = (float)xv;
           }
           w0 += tot;
@@ -2290,7 +2413,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     std::iota(order.begin(), order.end(), 0);
     auto colof = [&](int32_t q) { return cols ? cols[q] : q; };
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
-      return m->h_colcnt[colof(x)] > m->h_colcnt[colof(y)];
+      return m->h_colcnt[m->h_rank[colof(x)]] > m->h_colcnt[m->h_rank[colof(y)]];
     });
 
     // ---- launch plan ---------------------------------------------------------------------------
@@ -2404,6 +2527,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     args.colval = m->d_colval;
     args.cnorms = m->d_cnorms;
     args.csq = m->d_csq;
+    args.rank = m->d_rank;
+    args.inv = m->d_inv;
     args.l1r = p.l1r;
     args.l2r = p.l2r;
     args.opttol = p.opttol;
@@ -2457,7 +2582,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         if (round >= kMaxPools) throw EngineError(kErr, "learn: output pool retry limit");
         const int32_t nt = (int32_t)pending.size();
         std::vector<int32_t> tcols(nt);
-        for (int32_t k = 0; k < nt; k++) tcols[k] = colof(pending[k]);
+        for (int32_t k = 0; k < nt; k++) tcols[k] = m->h_rank[colof(pending[k])];  // internal ids
         DevBuf<int32_t> d_targets, d_queue, d_ocnt, d_nit, d_nact;
         DevBuf<int64_t> d_ooff, d_an, d_ex;
         DevBuf<double> d_rn, d_ob;
@@ -2579,10 +2704,27 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         d_po.alloc(nsel);
         CK(cudaMemcpyAsync(d_so.p, src_off.data(), sizeof(int64_t) * nsel, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(d_po.p, pool_of.data(), sizeof(int32_t) * nsel, cudaMemcpyHostToDevice, s));
+        // the kernels emit each column in INTERNAL id order; the model wants ascending original ids
+        // (estimate.c:497-503): gather, then sort every column segment by its (original) row ids
+        DevBuf<int32_t> d_ti;
+        DevBuf<float> d_tv;
+        d_ti.alloc(res->nnz);
+        d_tv.alloc(res->nnz);
         gather_columns_kernel<<<grid_for((int64_t)nsel * 32, 256, m->sm_count), 256, 0, s>>>(
-            nsel, d_so.p, d_po.p, res->d_colptr, tab, res->d_colind, res->d_colval, res->d_counts);
+            nsel, d_so.p, d_po.p, res->d_colptr, tab, d_ti.p, d_tv.p, res->d_counts);
         CK(cudaGetLastError());
         res->tm.launches++;
+        if (res->nnz > 0) {
+          size_t tmp_bytes = 0;
+          CK(cub::DeviceSegmentedSort::SortPairs(nullptr, tmp_bytes, d_ti.p, res->d_colind, d_tv.p, res->d_colval,
+                                                 res->nnz, (int64_t)nsel, res->d_colptr, res->d_colptr + 1, s));
+          DevBuf<unsigned char> d_tmp;
+          d_tmp.alloc(tmp_bytes);
+          CK(cub::DeviceSegmentedSort::SortPairs(d_tmp.p, tmp_bytes, d_ti.p, res->d_colind, d_tv.p, res->d_colval,
+                                                 res->nnz, (int64_t)nsel, res->d_colptr, res->d_colptr + 1, s));
+          res->tm.launches += 2;
+          CK(cudaStreamSynchronize(s));
+        }
         CK(cudaStreamSynchronize(s));
       }
       CK(cudaEventRecord(e2, s));

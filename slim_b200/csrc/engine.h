@@ -46,7 +46,9 @@ void matrix_info(const Matrix *m, int32_t *nrows, int32_t *ncols, int64_t *nnz, 
 int matrix_csc_to_host(const Matrix *m, int64_t *colptr, int32_t *colind, float *colval,
                        float *cnorms);
 
-// Window Gram blocks (tests): double[ceil(ncols/32)][32][32].
+// Internal item order (tests): rank[original id] = internal id (items sorted by descending nnz).
+int matrix_item_order_to_host(const Matrix *m, int32_t *rank);
+// Window Gram blocks in INTERNAL item order (tests): double[ceil(ncols/32)][32][32].
 int matrix_window_gram_to_host(const Matrix *m, double *out);
 
 Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel,

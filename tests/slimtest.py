@@ -187,7 +187,7 @@ class _OStats(C.Structure):
                 ("rnorm", C.POINTER(C.c_double)), ("objval", C.POINTER(C.c_double))]
 
 
-ORDER_ASCENDING, ORDER_REF_RAND = 0, 1
+ORDER_ASCENDING, ORDER_REF_RAND, ORDER_POPULARITY = 0, 1, 2
 
 
 class Oracle:

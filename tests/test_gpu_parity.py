@@ -98,6 +98,11 @@ def test_window_gram_blocks(lib, ratings):
     G = (R.T @ R).toarray()
     with Staged(rp, ri, rv) as s:
         got = s.window_gram()
+        rank = s.item_order()
+    cnt = np.bincount(ri, minlength=200)
+    inv = np.lexsort((np.arange(200), -cnt))  # descending nnz, ties by ascending id
+    assert np.array_equal(rank[inv], np.arange(200))
+    G = G[np.ix_(inv, inv)]  # Gram matrix in the engine's internal item order
     assert got.shape == (7, 32, 32)
     for w in range(7):
         n = min(32, 200 - 32 * w)
@@ -141,7 +146,7 @@ def test_default_setting_matches_oracle_same_order(lib, ours, oracle, name):
     g = st.load_golden(name)
     h = _learn(ours, g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"])
     mv = st.model_views(h)
-    w = oracle.learn(g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], nthreads=8)
+    w = oracle.learn(g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], nthreads=8, order=st.ORDER_POPULARITY)
     _check_close(mv, w, tol=1e-6)
     # and against the reference's own (shuffled-order) result at its self-noise level
     maxd, _ = st.compare_models(mv, _golden_model(g, "default"))
@@ -160,7 +165,7 @@ def test_kernel_variants_small(lib, ours, oracle, monkeypatch, nt, yglobal, rati
         rv = None
     kw = dict(l1r=0.7, l2r=1.5, **CONV)
     h = _learn(ours, rp, ri, rv, **kw)
-    w = oracle.learn(rp, ri, rv, nthreads=8, **kw)
+    w = oracle.learn(rp, ri, rv, nthreads=8, **kw, order=st.ORDER_POPULARITY)
     _check_close(st.model_views(h), w)
     ours.free(h)
 
@@ -179,7 +184,7 @@ def test_cluster_kernel_variants(lib, ours, oracle, monkeypatch, cs, window, rat
         rv = None
     kw = dict(l1r=0.7, l2r=1.5, **CONV)
     h = _learn(ours, rp, ri, rv, **kw)
-    w = oracle.learn(rp, ri, rv, nthreads=8, **kw)
+    w = oracle.learn(rp, ri, rv, nthreads=8, **kw, order=st.ORDER_POPULARITY)
     _check_close(st.model_views(h), w)
     ours.free(h)
 
@@ -211,7 +216,7 @@ def test_long_columns_and_iteration_cap(lib, ours, oracle, monkeypatch, cs, wind
     with Staged(rp, ri, rv) as s:
         r = learn_columns(s, dict(niters=50), cols=cols)
         got, stats = r.to_host(), r.stats()
-    ref = oracle.learn(rp, ri, rv, niters=50, cols=cols, nthreads=8, want_stats=True)
+    ref = oracle.learn(rp, ri, rv, niters=50, cols=cols, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
     assert np.array_equal(stats["nactive"], ref["stats"]["nactive"])
     assert np.array_equal(stats["active_nnz"], ref["stats"]["active_nnz"])
     assert np.array_equal(stats["expand_nnz"], ref["stats"]["expand_nnz"])
@@ -229,7 +234,7 @@ def test_warm_start(lib, ours, oracle, monkeypatch, cs):
     m0 = st.model_views(h0)
     h1 = _learn(ours, rp, ri, rv, imodel=h0, l1r=1.0, l2r=1.0, niters=5)
     w1 = oracle.learn(rp, ri, rv, l1r=1.0, l2r=1.0, niters=5, nthreads=4,
-                      imodel=(m0["ncols"], m0["colptr"], m0["colind"], m0["colval"]))
+                      imodel=(m0["ncols"], m0["colptr"], m0["colind"], m0["colval"]), order=st.ORDER_POPULARITY)
     _check_close(st.model_views(h1), w1, tol=1e-6)
     # 5 sweeps from a warm start differ from 5 cold sweeps: the warm start was really used
     hc = _learn(ours, rp, ri, rv, l1r=1.0, l2r=1.0, niters=5)
@@ -246,7 +251,7 @@ def test_window_sweep_large_and_small_columns(lib, ours, oracle, monkeypatch):
 
     rp, ri, rv = st.synth_zipf(40000, 600, 30, seed=77)
     cols = np.arange(0, 600, 13, dtype=np.int32)
-    ref = oracle.learn(rp, ri, rv, niters=30, cols=cols, nthreads=8, want_stats=True)
+    ref = oracle.learn(rp, ri, rv, niters=30, cols=cols, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
     for cs in ("1", "4", "16"):
         monkeypatch.setenv("SLIMB200_CLUSTER", cs)
         with Staged(rp, ri, rv) as s:
@@ -266,7 +271,7 @@ def test_edge_cases(lib, ours, oracle):
     for kw in (dict(l1r=0.1, l2r=0.5), dict(l1r=0.1, l2r=0.5, niters=0), dict(l1r=0.0, l2r=0.0)):
         h = _learn(ours, rp, ri, rv, **kw)
         mv = st.model_views(h)
-        w = oracle.learn(rp, ri, rv, **{**dict(opttol=1e-7, niters=10000), **kw})
+        w = oracle.learn(rp, ri, rv, **{**dict(opttol=1e-7, niters=10000, order=st.ORDER_POPULARITY), **kw})
         assert mv["ncols"] == 4
         _check_close(mv, w, tol=1e-6)
         ours.free(h)
@@ -312,7 +317,7 @@ def test_medium_synthetic_objective_property(lib, oracle):
     assert (stats["objval"] <= 0.5 * cnt + 1e-6).all()
     order = np.argsort(cnt, kind="stable")
     sample = np.sort(order[:: len(order) // 48]).astype(np.int32)
-    ref = oracle.learn(rp, ri, rv, niters=50, cols=sample, nthreads=8, want_stats=True)
+    ref = oracle.learn(rp, ri, rv, niters=50, cols=sample, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
     assert np.allclose(stats["objval"][sample], ref["stats"]["objval"], rtol=1e-6)
     sub = dict(colptr=np.concatenate([[0], np.cumsum(np.diff(w["colptr"])[sample])]),
                colind=np.concatenate([w["colind"][w["colptr"][j]:w["colptr"][j + 1]] for j in sample]),

@@ -51,6 +51,20 @@ def test_ascending_mode_matches_converged_golden(oracle, name):
     assert np.array_equal(np.round(got, 4), np.round(g["metrics"], 4)), (got, g["metrics"])
 
 
+def test_popularity_order_mode(oracle):
+    # a different FIXED visiting order (the CUDA engine's) reaches the same optimum
+    g = st.load_golden("automotive")
+    w = oracle.learn(g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], nthreads=8,
+                     order=st.ORDER_POPULARITY, **CONV)
+    maxd, flips = st.compare_models(w, _golden_model(g, "conv"))
+    assert maxd <= TOL and all(mag < TOL for _, _, mag in flips)
+    # ... and differs from the ascending order when the sweeps are capped (order matters off the optimum)
+    a = oracle.learn(g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], niters=2, nthreads=8)
+    b = oracle.learn(g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], niters=2, nthreads=8,
+                     order=st.ORDER_POPULARITY)
+    assert st.compare_models(a, b)[0] > 1e-6
+
+
 def test_golden_values_are_the_surveyed_ones(ml100k, automotive):
     assert len(ml100k["W_conv_colind"]) == 65909
     assert len(automotive["W_conv_colind"]) == 84317
