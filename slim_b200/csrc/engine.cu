@@ -348,29 +348,48 @@ __global__ void column_split_kernel(int32_t ncols, int32_t rows_per_part, const 
 // would (see cd_window_kernel).  One CTA per window at a time; a user-indexed bit mask (which columns
 // of the window contain user u) finds the overlapping pairs, which are rare for sparse columns.
 template <bool HASVAL>
-__global__ void window_gram_kernel(int32_t ncols, int32_t nwin, const int64_t *__restrict__ colptr,
-                                   const int32_t *__restrict__ colcnt, const int32_t *__restrict__ colind,
-                                   const float *__restrict__ colval, uint32_t *masks, size_t mask_stride,
-                                   double *wgram) {
+__global__ void window_gram_kernel(int32_t ncols, int32_t nrows, int32_t nitems, const int32_t *__restrict__ item_w,
+                                   const int32_t *__restrict__ item_s, const int32_t *__restrict__ item_S,
+                                   const int64_t *__restrict__ colptr, const int32_t *__restrict__ colcnt,
+                                   const int32_t *__restrict__ colind, const float *__restrict__ colval,
+                                   uint32_t *masks, size_t mask_stride, double *wgram) {
+  // One work item = (window, user slice): dense head windows are split over many CTAs by user range.
   uint32_t *mask = masks + (size_t)blockIdx.x * mask_stride;
   __shared__ double g[32][33];
+  __shared__ int e_lo[32], e_hi[32];
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int w = blockIdx.x; w < nwin; w += gridDim.x) {
+  for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int w = item_w[it], sl = item_s[it], S = item_S[it];
+    const int64_t u_lo = (int64_t)nrows * sl / S, u_hi = (int64_t)nrows * (sl + 1) / S;
     for (int t = tid; t < 32 * 33; t += nt) (&g[0][0])[t] = 0.0;
     const int cbase = w * 32;
     const int nc = min(32, ncols - cbase);
+    if (tid < 32) {  // entry range of column tid inside the user slice (users ascend inside a column)
+      int lo = 0, hi = 0;
+      if (tid < nc) {
+        const int32_t *ix = colind + colptr[cbase + tid];
+        const int cnt = colcnt[cbase + tid];
+        int a0 = 0, a1 = cnt;
+        while (a0 < a1) { const int mid = (a0 + a1) >> 1; if ((int64_t)ix[mid] < u_lo) a0 = mid + 1; else a1 = mid; }
+        lo = a0;
+        a1 = cnt;
+        while (a0 < a1) { const int mid = (a0 + a1) >> 1; if ((int64_t)ix[mid] < u_hi) a0 = mid + 1; else a1 = mid; }
+        hi = a0;
+      }
+      e_lo[tid] = lo;
+      e_hi[tid] = hi;
+    }
+    __syncthreads();
     // pass 1: set bit k of mask[u] for every entry (u) of column k
     for (int k = 0; k < nc; k++) {
       const int64_t c0 = colptr[cbase + k];
-      const int cnt = colcnt[cbase + k];
-      for (int e = tid; e < cnt; e += nt) atomicOr(&mask[colind[c0 + e]], 1u << k);
+      for (int e = e_lo[k] + tid; e < e_hi[k]; e += nt) atomicOr(&mask[colind[c0 + e]], 1u << k);
     }
     __syncthreads();
     // pass 2: every user shared by columns k > m contributes v_ku * v_mu to G[k][m]
     for (int k = 0; k < nc; k++) {
       const int64_t c0 = colptr[cbase + k];
-      const int cnt = colcnt[cbase + k];
-      for (int e = tid; e < cnt; e += nt) {
+      for (int e = e_lo[k] + tid; e < e_hi[k]; e += nt) {
         const int u = colind[c0 + e];
         uint32_t lower = __ldcg(&mask[u]) & ((1u << k) - 1u);  // L2: the atomics above bypass L1
         const double vk = HASVAL ? (double)colval[c0 + e] : 1.0;
@@ -392,18 +411,25 @@ __global__ void window_gram_kernel(int32_t ncols, int32_t nwin, const int64_t *_
       }
     }
     __syncthreads();
-    // pass 3: clear the mask for the next window, write the (symmetric) block
+    // pass 3: clear the mask for the next work item, accumulate the (lower triangular) block
     for (int k = 0; k < nc; k++) {
       const int64_t c0 = colptr[cbase + k];
-      const int cnt = colcnt[cbase + k];
-      for (int e = tid; e < cnt; e += nt) mask[colind[c0 + e]] = 0u;
+      for (int e = e_lo[k] + tid; e < e_hi[k]; e += nt) mask[colind[c0 + e]] = 0u;
     }
     double *out = wgram + (size_t)w * 1024;
     for (int t = tid; t < 1024; t += nt) {
       const int k = t >> 5, mcol = t & 31;
-      out[t] = k > mcol ? g[k][mcol] : (k < mcol ? g[mcol][k] : 0.0);
+      if (k > mcol && g[k][mcol] != 0.0) atomicAdd(&out[t], g[k][mcol]);
     }
     __syncthreads();
+  }
+}
+
+__global__ void window_gram_symmetrize_kernel(int32_t nwin, double *wgram) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nwin * 1024;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)((t >> 5) & 31), mcol = (int)(t & 31);
+    if (k < mcol) wgram[t] = wgram[(t & ~(int64_t)1023) + mcol * 32 + k];
   }
 }
 
@@ -595,20 +621,44 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
     if (ncols > 0) {
       const int32_t nwin = (ncols + 31) / 32;
       CK(cudaMalloc(&m->d_wgram, sizeof(double) * (size_t)nwin * 1024));
-      const int gw = std::max(1, std::min(nwin, m->sm_count * 2));
+      CK(cudaMemsetAsync(m->d_wgram, 0, sizeof(double) * (size_t)nwin * 1024, s));
+      // work items: (window, user slice); a window with many entries is split by user range
+      std::vector<int32_t> iw, is, iS;
+      for (int32_t w = 0; w < nwin; w++) {
+        int64_t tot = 0;
+        for (int32_t c = w * 32; c < std::min(ncols, w * 32 + 32); c++) tot += m->h_colcnt[c];
+        const int32_t S = (int32_t)std::max<int64_t>(1, std::min<int64_t>(128, (tot + 131071) / 131072));
+        for (int32_t sl = 0; sl < S; sl++) {
+          iw.push_back(w);
+          is.push_back(sl);
+          iS.push_back(S);
+        }
+      }
+      const int32_t nitems = (int32_t)iw.size();
+      DevBuf<int32_t> d_iw, d_is, d_iS;
+      d_iw.alloc(nitems);
+      d_is.alloc(nitems);
+      d_iS.alloc(nitems);
+      CK(cudaMemcpyAsync(d_iw.p, iw.data(), sizeof(int32_t) * nitems, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_is.p, is.data(), sizeof(int32_t) * nitems, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_iS.p, iS.data(), sizeof(int32_t) * nitems, cudaMemcpyHostToDevice, s));
+      const int gw = std::max(1, std::min(nitems, m->sm_count * 2));
       const size_t mask_stride = ((size_t)std::max(nrows, 1) + 3) & ~size_t(3);
       DevBuf<uint32_t> d_masks;
       d_masks.alloc_zero((size_t)gw * mask_stride, s);
       const bool kv = m->has_val && !m->unit;
       if (kv)
-        window_gram_kernel<true><<<gw, 512, 0, s>>>(ncols, nwin, m->d_colptr, m->d_colcnt, m->d_colind,
-                                                    m->d_colval, d_masks.p, mask_stride, m->d_wgram);
+        window_gram_kernel<true><<<gw, 512, 0, s>>>(ncols, nrows, nitems, d_iw.p, d_is.p, d_iS.p, m->d_colptr,
+                                                    m->d_colcnt, m->d_colind, m->d_colval, d_masks.p, mask_stride,
+                                                    m->d_wgram);
       else
-        window_gram_kernel<false><<<gw, 512, 0, s>>>(ncols, nwin, m->d_colptr, m->d_colcnt, m->d_colind,
-                                                     nullptr, d_masks.p, mask_stride, m->d_wgram);
-      m->stage_launches++;
+        window_gram_kernel<false><<<gw, 512, 0, s>>>(ncols, nrows, nitems, d_iw.p, d_is.p, d_iS.p, m->d_colptr,
+                                                     m->d_colcnt, m->d_colind, nullptr, d_masks.p, mask_stride,
+                                                     m->d_wgram);
+      window_gram_symmetrize_kernel<<<grid_for((int64_t)nwin * 1024, 256, m->sm_count), 256, 0, s>>>(nwin, m->d_wgram);
+      m->stage_launches += 2;
       CK(cudaGetLastError());
-      CK(cudaStreamSynchronize(s));  // d_masks is released at scope exit
+      CK(cudaStreamSynchronize(s));  // staging buffers are released at scope exit
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, s));
