@@ -110,6 +110,7 @@ struct Matrix {
   int32_t nrows = 0, ncols = 0;
   int64_t nnz = 0, nnzp = 0;
   bool has_val = false;   // the caller passed a value array
+  bool nonneg = true;     // no stored value is negative (Gram blocks >= 0: lets the window solve skip slots)
   bool unit = false;      // ... and every stored value is exactly 1.0f: the kernels then skip the value
                           // stream (4 B per nonzero instead of 8), same arithmetic as the binary path
   // Items are RELABELED by popularity inside the engine: internal id = position of the item when items
@@ -312,12 +313,15 @@ __global__ void column_norms_kernel(int32_t ncols, const int64_t *__restrict__ c
 
 constexpr int kParts = 16;  // user ranges per column = largest cluster size
 
-__global__ void all_ones_kernel(const float *__restrict__ v, int64_t n, int32_t *not_one) {
-  bool bad = false;
+__global__ void all_ones_kernel(const float *__restrict__ v, int64_t n, int32_t *flags) {
+  bool bad = false, neg = false;  // flags bit 0: some value != 1, bit 1: some value < 0 (or NaN)
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
-       k += (int64_t)gridDim.x * blockDim.x)
+       k += (int64_t)gridDim.x * blockDim.x) {
     bad |= (v[k] != 1.0f);
-  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(not_one, 1);
+    neg |= !(v[k] >= 0.0f);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1);
+  if (__any_sync(0xffffffffu, neg) && (threadIdx.x & 31) == 0) atomicOr(flags, 2);
 }
 
 // colsplit[c][r] = number of entries of column c whose user id is < r * rows_per_part.  Users are
@@ -602,7 +606,8 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
       CK(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
       const bool keep = getenv("SLIMB200_KEEP_VALUES") && atoi(getenv("SLIMB200_KEEP_VALUES"));
-      if (flag == 0 && !keep) {
+      m->nonneg = (flag & 2) == 0;
+      if ((flag & 1) == 0 && !keep) {
         m->unit = true;
         cudaFree(m->d_rowval);
         cudaFree(m->d_colval);
@@ -1166,6 +1171,7 @@ struct ClusterArgs {
   double *xc;           // per CTA [col_stride]: every CTA keeps its own copy of x (identical values)
   int32_t rows_per_part;
   const double *wgram;  // window Gram blocks (staging)
+  int32_t nonneg;       // all ratings >= 0: Gram blocks are >= 0
   GroupMeta *groups;    // per cluster [grp_stride]
   size_t grp_stride;
 };
@@ -1259,10 +1265,10 @@ struct __align__(16) RoundTab {
   long long c0[32];   // padded offset of the column of slot b
   double inv_den[32]; // 1 / (cnorm^2 + l2r)
   double sq[32];      // exact sum of squares
-  int s0[32], s1[32]; // this CTA's entry range in the column
-  int soff[32];       // first 16-byte chunk of the staged copy in the stage buffer, -1: not staged
-  int p[32];          // position in the active list (x[p])
+  int4 rec[32];       // .x/.y: this CTA's entry range [s0, s1) in the column; .z: first 16-byte chunk of the
+                      // staged copy in the stage buffer (-1: not staged); .w: position in the active list (x[p])
   float aty[32];
+  signed char wfast[kClusterNT / 32];     // consumer warp w: all its columns are staged, <= 1 chunk per lane
   signed char wslot[kClusterNT / 32][8];  // the (up to kWarpSlots) small columns gathered by consumer warp w, -1: none
   signed char abit[32];                   // active slots in ascending order (the solve's visiting order)
   unsigned mask;      // active slots
@@ -1750,14 +1756,12 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
         RoundTab &T = ps.tab[r % 3];
         const unsigned mask = (unsigned)R.gm.y;
         const bool act = (mask >> lane) & 1u;
-        int nch = 0;
+        int nch = 0, slot_p = 0;
         bool small = false;
         if (act) {
           const double den = __hiloint2double(R.h1.y, R.h1.x);
           T.c0[lane] = (long long)(((unsigned long long)(unsigned)R.h0.y << 32) | (unsigned)R.h0.x);
-          T.s0[lane] = R.sp0;
-          T.s1[lane] = R.sp1;
-          T.p[lane] = R.gm.z + __popc(mask & ((1u << lane) - 1u));
+          slot_p = R.gm.z + __popc(mask & ((1u << lane) - 1u));
           T.aty[lane] = __int_as_float(R.h0.w);
           T.inv_den[lane] = 1.0 / den;
           T.sq[lane] = __hiloint2double(R.h1.w, R.h1.z);
@@ -1771,7 +1775,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
           if (lane >= o) pre += up;
         }
         const bool staged = small && pre <= CAP;  // pre is the inclusive prefix
-        T.soff[lane] = staged ? pre - want : -1;
+        T.rec[lane] = make_int4(act ? R.sp0 : 0, act ? R.sp1 : 0, staged ? pre - want : -1, slot_p);
         // work lists: the ord-th small column goes to consumer warp ord % NCW; big columns to the whole CTA
         for (int k = lane; k < 8 * NW; k += 32) (&T.wslot[0][0])[k] = -1;
         __syncwarp();
@@ -1780,6 +1784,21 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
         if (small) {
           const int ord = __popc(smask & ((1u << lane) - 1u));
           T.wslot[ord % NCW][ord / NCW] = (signed char)lane;
+        }
+        {  // per consumer warp: can it take the one-chunk-per-lane fast path for all its columns?
+          const unsigned slow = __ballot_sync(0xffffffffu, small && !(staged && nch <= 32));
+          if (lane < NW) {
+            unsigned mine = 0u;
+            for (int o = lane; o < 32; o += NCW) mine |= 1u << o;   // ords of warp `lane`
+            // slot bit -> ord: the ord-th set bit of smask
+            bool ok = true;
+            for (unsigned mm = slow; mm; mm &= mm - 1) {
+              const int b = __ffs(mm) - 1;
+              const int ord = __popc(smask & ((1u << b) - 1u));
+              if ((mine >> ord) & 1u) ok = false;
+            }
+            T.wfast[lane] = ok ? 1 : 0;
+          }
         }
         if (act) T.abit[__popc(mask & ((1u << lane) - 1u))] = (signed char)lane;
         int tot = staged ? nch : 0;
@@ -1799,12 +1818,13 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
         const RoundTab &T = ps.tab[r % 3];
         if (lane == 0) mbar_expect_tx(&ps.mbar[buf], T.bytes + 8192u);
         __syncwarp();
-        if (((T.mask >> lane) & 1u) && T.soff[lane] >= 0) {
-          const int ch0 = T.s0[lane] >> 2, nch = ((T.s1[lane] + 3) >> 2) - ch0;
-          bulk_g2s(&ps.sidx[buf][T.soff[lane]], a.colind + T.c0[lane] + 4 * (int64_t)ch0, (uint32_t)nch * 16u,
+        const int4 rc = T.rec[lane];
+        if (((T.mask >> lane) & 1u) && rc.z >= 0) {
+          const int ch0 = rc.x >> 2, nch = ((rc.y + 3) >> 2) - ch0;
+          bulk_g2s(&ps.sidx[buf][rc.z], a.colind + T.c0[lane] + 4 * (int64_t)ch0, (uint32_t)nch * 16u,
                    &ps.mbar[buf]);
           if (HASVAL)
-            bulk_g2s(&ps.sval[buf][T.soff[lane]], a.colval + T.c0[lane] + 4 * (int64_t)ch0, (uint32_t)nch * 16u,
+            bulk_g2s(&ps.sval[buf][rc.z], a.colval + T.c0[lane] + 4 * (int64_t)ch0, (uint32_t)nch * 16u,
                      &ps.mbar[buf]);
         }
         if (lane == 0) bulk_g2s(&ps.G[buf][0][0], ca.wgram + (size_t)T.win * 1024, 8192u, &ps.mbar[buf]);
@@ -1840,7 +1860,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
           const RoundTab &T = ps.tab[r % 3];
           const unsigned mask = T.mask;
           double xi = 0.0;
-          if (warp == 0 && ((mask >> lane) & 1u)) xi = x[T.p[lane]];  // consumed by the solve
+          if (warp == 0 && ((mask >> lane) & 1u)) xi = x[T.rec[lane].w];  // consumed by the solve
           if (warp == NW - 1) {
             tab_load(gm_ahead, treg);       // start reading the coordinate lines of round r + 2 ...
             gm_ahead = group_rec(r + 3);    // ... and the window record of round r + 3
@@ -1855,30 +1875,28 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
             SLIM_TICK(5);
             if (warp < NCW && T.wslot[warp][0] >= 0) {
               int myb[kWarpSlots];
+              {
+                const long long packed = *reinterpret_cast<const long long *>(&T.wslot[warp][0]);
 #pragma unroll
-              for (int k = 0; k < kWarpSlots; k++) myb[k] = T.wslot[warp][k];
-              // fast path: every column is staged with at most one 16-byte chunk per lane -- all yhat
-              // gathers (L2 latency) of all the warp's columns are issued before the first reduction
-              auto one_chunk = [&](int b) {
-                return b < 0 || (T.soff[b] >= 0 && ((T.s1[b] + 3) >> 2) - (T.s0[b] >> 2) <= 32) || T.s1[b] <= T.s0[b];
-              };
-              bool fast = true;
-#pragma unroll
-              for (int k = 0; k < kWarpSlots; k++) fast = fast && one_chunk(myb[k]);
+                for (int k = 0; k < kWarpSlots; k++) myb[k] = (int)(signed char)((packed >> (8 * k)) & 0xff);
+              }
               SLIM_TICK(5);
-              if (fast) {
+              if (T.wfast[warp]) {
+                // fast path: every column is staged with at most one 16-byte chunk per lane -- all yhat
+                // gathers (L2 latency) of all the warp's columns are issued before the first reduction
                 double pv[kWarpSlots];
 #pragma unroll
                 for (int k = 0; k < kWarpSlots; k++) {
                   const int b = myb[k];
                   double v = 0.0;
-                  if (b >= 0 && T.s1[b] > T.s0[b]) {
-                    const int s0 = T.s0[b], s1 = T.s1[b], ch0 = s0 >> 2, nch = ((s1 + 3) >> 2) - ch0;
+                  if (b >= 0) {
+                    const int4 rc = T.rec[b];
+                    const int ch0 = rc.x >> 2, nch = ((rc.y + 3) >> 2) - ch0;
                     if (lane < nch) {
                       Chunk c;
-                      c.ix = ps.sidx[buf][T.soff[b] + lane];
-                      if (HASVAL) c.vv = ps.sval[HASVAL ? buf : 0][HASVAL ? T.soff[b] + lane : 0];
-                      v = dot_chunk_r<HASVAL, true>(c, (ch0 + lane) * 4, s0, s1, yh);
+                      c.ix = ps.sidx[buf][rc.z + lane];
+                      if (HASVAL) c.vv = ps.sval[HASVAL ? buf : 0][HASVAL ? rc.z + lane : 0];
+                      v = dot_chunk_r<HASVAL, true>(c, (ch0 + lane) * 4, rc.x, rc.y, yh);
                     }
                   }
                   pv[k] = v;
@@ -1902,11 +1920,10 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
                 for (int k = 0; k < kWarpSlots; k++) {
                   const int b = myb[k];
                   if (b < 0) continue;
-                  const int s0 = T.s0[b], s1 = T.s1[b];
-                  if (s1 <= s0) continue;
-                  const int so = T.soff[b];
-                  const double v = so >= 0 ? warp_dot_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, yh)
-                                           : warp_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
+                  const int4 rc = T.rec[b];
+                  if (rc.y <= rc.x) continue;
+                  const double v = rc.z >= 0 ? warp_dot_staged<HASVAL>(&ps.sidx[buf][rc.z], &ps.sval[HASVAL ? buf : 0][HASVAL ? rc.z : 0], rc.x, rc.y, yh)
+                                             : warp_dot<HASVAL>(a, T.c0[b], rc.x, rc.y, yh);
                   if (lane == 0) ps.pcta[xb][b] = v;
                 }
               }
@@ -1914,7 +1931,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
             SLIM_TICK(6);
             for (unsigned mm = T.bigmask; mm; mm &= mm - 1) {
               const int b = __ffs(mm) - 1;
-              const int s0 = T.s0[b], s1 = T.s1[b];
+              const int s0 = T.rec[b].x, s1 = T.rec[b].y;
               {
                 double v = block_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
 #pragma unroll
@@ -1953,8 +1970,6 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
             const double inv_den = act ? T.inv_den[lane] : 0.0;
             const double sqv = act ? T.sq[lane] : 0.0;
             const int nact = T.nact;
-            int mb = T.abit[0];
-            double grow = ps.G[buf][mb][lane];
             ps.pcta[xb ^ 1u][lane] = 0.0;  // clear the other buffer for the next round
             double P = 0.0;  // poll until the tagged partials of all CTAs have landed (fixed summation order)
             for (int c = 0; c < cs; c++) P += ld_tagged_wait(&ps.pall[xb][c][lane][0], xr + 1u);
@@ -1976,24 +1991,34 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
             const double cthr = aty - a.l1r;      // x' = max(cthr - ip, 0) * inv_den
             const double den = act ? 1.0 / inv_den : 1.0;
             const double qeps = kEps * den;       // |x'| > EPS  <=>  q > EPS * den   (q >= 0)
-            double nx = xi, d = 0.0;
-            for (int k = 0; k < nact; k++) {
-              const int mb_next = T.abit[k + 1 < nact ? k + 1 : k];
-              const double grow_next = ps.G[buf][mb_next][lane];
-              // slot mb: q = numerator of the update; broadcast q*inv_den when it enters yhat, else 0
-              const double q = cthr - ip;
-              const double xq = q > 0.0 ? q * inv_den : 0.0;
-              const double inn = q > qeps ? xq : 0.0;
-              const double in_new_b = __shfl_sync(0xffffffffu, inn, mb);
-              if (lane == mb) {
-                nx = xq;
-                d = inn - in_old;
+            double nx = act ? 0.0 : xi, d = act ? -in_old : 0.0;  // default: the slot ends at zero
+            // With non-negative ratings G >= 0 and every step adds in_new >= 0 times a Gram entry, so ip can
+            // only GROW along the chain: a slot whose numerator is already <= 0 ends at exactly zero and
+            // contributes nothing to later slots.  Only the remaining candidates form the dependent chain
+            // (after the first sweeps that is a small fraction of the window).
+            unsigned cand = __ballot_sync(0xffffffffu, act && (ca.nonneg ? (cthr - ip > 0.0) : true));
+            if (cand) {
+              int mbc = __ffs(cand) - 1;
+              double growc = ps.G[buf][mbc][lane];
+              while (cand) {
+                cand &= cand - 1;
+                const int mb_next = cand ? __ffs(cand) - 1 : mbc;
+                const double grow_next = ps.G[buf][mb_next][lane];
+                // slot mbc: q = numerator of the update; broadcast q*inv_den when it enters yhat, else 0
+                const double q = cthr - ip;
+                const double xq = q > 0.0 ? q * inv_den : 0.0;
+                const double inn = q > qeps ? xq : 0.0;
+                const double in_new_b = __shfl_sync(0xffffffffu, inn, mbc);
+                if (lane == mbc) {
+                  nx = xq;
+                  d = inn - in_old;
+                }
+                ip = fma(in_new_b, growc, ip);  // only later slots still use ip; the diagonal of G is zero
+                mbc = mb_next;
+                growc = grow_next;
               }
-              ip = fma(in_new_b, grow, ip);  // only later slots still use ip; the diagonal of G is zero
-              mb = mb_next;
-              grow = grow_next;
             }
-            if (act) x[T.p[lane]] = nx;
+            if (act) x[T.rec[lane].w] = nx;
             ps.dlt[lane] = act ? d : 0.0;
             double dd = act ? (nx - xi) * (nx - xi) : 0.0;
 #pragma unroll
@@ -2012,9 +2037,10 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
               const int b = T.wslot[warp][k];
               if (b < 0) break;
               const double d = ps.dlt[b];
-              const int s0 = T.s0[b], s1 = T.s1[b];
+              const int4 rc = T.rec[b];
+              const int s0 = rc.x, s1 = rc.y;
               if (d != 0.0 && s1 > s0) {
-                const int so = T.soff[b];
+                const int so = rc.z;
                 if (so >= 0) warp_axpy_staged<HASVAL>(&ps.sidx[buf][so], &ps.sval[HASVAL ? buf : 0][HASVAL ? so : 0], s0, s1, d, yh);
                 else warp_axpy<HASVAL>(a, T.c0[b], s0, s1, d, yh);
               }
@@ -2023,7 +2049,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
           for (unsigned mm = T.bigmask; mm; mm &= mm - 1) {
             const int b = __ffs(mm) - 1;
             const double d = ps.dlt[b];
-            if (d != 0.0) block_axpy<HASVAL>(a, T.c0[b], T.s0[b], T.s1[b], d, yh);
+            if (d != 0.0) block_axpy<HASVAL>(a, T.c0[b], T.rec[b].x, T.rec[b].y, d, yh);
           }
           SLIM_TICK(10);
           if (warp == NW - 1) tab_store(r + 2, treg);  // ... consumed here, a whole round later
@@ -2597,6 +2623,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     cargs.xc = reinterpret_cast<double *>(sb + o_x);
     cargs.rows_per_part = m->rows_per_part;
     cargs.wgram = m->d_wgram;
+    cargs.nonneg = m->nonneg ? 1 : 0;
     cargs.groups = reinterpret_cast<GroupMeta *>(sb + o_grp);
     cargs.grp_stride = grp_stride;
     args.act_idx = reinterpret_cast<int32_t *>(sb + o_idx);
