@@ -1269,7 +1269,10 @@ struct __align__(16) RoundTab {
                       // staged copy in the stage buffer (-1: not staged); .w: position in the active list (x[p])
   float aty[32];
   signed char wfast[kClusterNT / 32];     // consumer warp w: all its columns are staged, <= 1 chunk per lane
-  signed char wslot[kClusterNT / 32][8];  // the (up to kWarpSlots) small columns gathered by consumer warp w, -1: none
+  int bigpre[32];     // big slots: first kBigBlk-entry block of the slot in the round's flattened block list
+  int bigtot;         // number of kBigBlk-entry blocks of all big slots
+  alignas(8) signed char wslot[kClusterNT / 32][8];  // the (up to kWarpSlots) small columns gathered by consumer
+                                                     // warp w (-1: none); read as one 8-byte word
   signed char abit[32];                   // active slots in ascending order (the solve's visiting order)
   unsigned mask;      // active slots
   unsigned bigmask;   // active slots whose range is too long for one warp: gathered by the whole CTA
@@ -1290,6 +1293,7 @@ struct __align__(128) PipeSmem {
   double pcta[2][32];                               // this CTA's partial inner products per slot (per exchange buffer)
   double dlt[32];                                   // yhat step per slot
   double pw[kClusterNT / 32];
+  double pwb[kClusterNT / 32][32];                  // per-warp partial inner products of the big slots
   double dl;
   unsigned long long mbar[2];                       // "stage buffer b has landed"
   unsigned long long xbar[2];                       // "all CTAs' partials of exchange buffer b have landed"
@@ -1462,28 +1466,99 @@ __device__ __forceinline__ void warp_axpy(const SolveArgs &a, int64_t c0, int s0
   }
 }
 
-// same over the whole CTA, 4 chunks in flight per thread
+// One block of kBigBlk entries [e0, e0+kBigBlk) of a column range [s0, s1) by one warp, "transposed":
+// gather / atomic instruction k covers the 32 CONSECUTIVE entries e0 + 32k .. e0 + 32k + 31 (ascending,
+// for dense head columns nearly consecutive users), so the lanes of an instruction share 32-byte yhat
+// sectors.  All id loads of the block are issued before the first gather and all gathers before the
+// first add: 16 loads in flight per lane hide the DRAM / L2 latency inside one warp.
+constexpr int kBigBlk = 512;
+constexpr int kBigShift = 9;
+constexpr int kBigPer = kBigBlk / 32;
+
+template <bool HASVAL>
+__device__ __forceinline__ double warp_bigblock_dot(const SolveArgs &a, int64_t c0, int s0, int s1, int e0,
+                                                    const double *yh) {
+  const int lane = threadIdx.x & 31;
+  const int32_t *ix = a.colind + c0;
+  const float *vv = HASVAL ? a.colval + c0 : nullptr;
+  const int lim = (s1 + 3) & ~3;  // padded columns are readable up to the next multiple of 4 entries
+  const int e = e0 + lane;
+  int id[kBigPer];
+  float vl[kBigPer];
+#pragma unroll
+  for (int k = 0; k < kBigPer; k++) {
+    id[k] = (e + 32 * k < lim) ? __ldg(ix + e + 32 * k) : 0;
+    if (HASVAL) vl[k] = (e + 32 * k >= s0 && e + 32 * k < s1) ? __ldg(vv + e + 32 * k) : 0.f;
+  }
+  double y[kBigPer];
+#pragma unroll
+  for (int k = 0; k < kBigPer; k++) y[k] = __ldcg(yh + id[k]);
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < kBigPer; k++) {
+    const bool ok = e + 32 * k >= s0 && e + 32 * k < s1;
+    acc += ok ? (HASVAL ? (double)vl[k] * y[k] : y[k]) : 0.0;
+  }
+  return acc;
+}
+
+template <bool HASVAL>
+__device__ __forceinline__ void warp_bigblock_axpy(const SolveArgs &a, int64_t c0, int s0, int s1, int e0, double d,
+                                                   double *yh) {
+  const int lane = threadIdx.x & 31;
+  const int32_t *ix = a.colind + c0;
+  const float *vv = HASVAL ? a.colval + c0 : nullptr;
+  const int lim = (s1 + 3) & ~3;
+  const int e = e0 + lane;
+  int id[kBigPer];
+  float vl[kBigPer];
+#pragma unroll
+  for (int k = 0; k < kBigPer; k++) {
+    id[k] = (e + 32 * k < lim) ? __ldg(ix + e + 32 * k) : 0;
+    if (HASVAL) vl[k] = (e + 32 * k >= s0 && e + 32 * k < s1) ? __ldg(vv + e + 32 * k) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < kBigPer; k++)
+    if (e + 32 * k >= s0 && e + 32 * k < s1) atomicAdd(yh + id[k], HASVAL ? d * (double)vl[k] : d);
+}
+
+// Same over the whole CTA for LONG column ranges.  Entries are taken "transposed": one gather / atomic
+// instruction of a warp covers 32 CONSECUTIVE entries of the column (ascending, for dense head columns
+// nearly consecutive users), so the lanes of an instruction share 32-byte yhat sectors instead of each
+// lane touching its own one -- up to 4x fewer L2 sector requests on the dense columns that dominate a
+// typical target.  4 x 32-bit id loads (each coalesced) replace one 128-bit load per lane.
 template <bool HASVAL>
 __device__ __forceinline__ double block_dot(const SolveArgs &a, int64_t c0, int s0, int s1, const double *yh) {
   constexpr int NT = kClusterNT;
-  const int ch1 = (s1 + 3) >> 2;
-  int ch = (s0 >> 2) + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t *ix = a.colind + c0;
+  const float *vv = HASVAL ? a.colval + c0 : nullptr;
+  const int e_begin = s0 & ~127;  // blocks of 128 entries, one block per warp per step
+  const int lim = (s1 + 3) & ~3;  // padded columns are readable up to the next multiple of 4 entries
   double part = 0.0;
-  for (; ch + 3 * NT < ch1; ch += 4 * NT) {
-    Chunk c0_, c1_, c2_, c3_;
-    load_chunk<HASVAL>(a, c0, ch, c0_);
-    load_chunk<HASVAL>(a, c0, ch + NT, c1_);
-    load_chunk<HASVAL>(a, c0, ch + 2 * NT, c2_);
-    load_chunk<HASVAL>(a, c0, ch + 3 * NT, c3_);
-    part += dot_chunk_r<HASVAL, true>(c0_, ch * 4, s0, s1, yh);
-    part += dot_chunk_r<HASVAL, true>(c1_, (ch + NT) * 4, s0, s1, yh);
-    part += dot_chunk_r<HASVAL, true>(c2_, (ch + 2 * NT) * 4, s0, s1, yh);
-    part += dot_chunk_r<HASVAL, true>(c3_, (ch + 3 * NT) * 4, s0, s1, yh);
-  }
-  for (; ch < ch1; ch += NT) {
-    Chunk c;
-    load_chunk<HASVAL>(a, c0, ch, c);
-    part += dot_chunk_r<HASVAL, true>(c, ch * 4, s0, s1, yh);
+  for (int e0 = e_begin + warp * 128; e0 < s1; e0 += (NT / 32) * 128) {
+    const int e = e0 + lane;
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    const bool k0 = e >= s0 && e < s1, k1 = e + 32 >= s0 && e + 32 < s1;
+    const bool k2 = e + 64 >= s0 && e + 64 < s1, k3 = e + 96 >= s0 && e + 96 < s1;
+    if (e < lim) i0 = __ldg(ix + e);
+    if (e + 32 < lim) i1 = __ldg(ix + e + 32);
+    if (e + 64 < lim) i2 = __ldg(ix + e + 64);
+    if (e + 96 < lim) i3 = __ldg(ix + e + 96);
+    if (HASVAL) {
+      if (k0) v0 = __ldg(vv + e);
+      if (k1) v1 = __ldg(vv + e + 32);
+      if (k2) v2 = __ldg(vv + e + 64);
+      if (k3) v3 = __ldg(vv + e + 96);
+    }
+    const double y0 = __ldcg(yh + i0), y1 = __ldcg(yh + i1), y2 = __ldcg(yh + i2), y3 = __ldcg(yh + i3);
+    double acc = 0.0;
+    acc += k0 ? (HASVAL ? (double)v0 * y0 : y0) : 0.0;
+    acc += k1 ? (HASVAL ? (double)v1 * y1 : y1) : 0.0;
+    acc += k2 ? (HASVAL ? (double)v2 * y2 : y2) : 0.0;
+    acc += k3 ? (HASVAL ? (double)v3 * y3 : y3) : 0.0;
+    part += acc;
   }
   return part;
 }
@@ -1491,23 +1566,19 @@ __device__ __forceinline__ double block_dot(const SolveArgs &a, int64_t c0, int 
 template <bool HASVAL>
 __device__ __forceinline__ void block_axpy(const SolveArgs &a, int64_t c0, int s0, int s1, double d, double *yh) {
   constexpr int NT = kClusterNT;
-  const int ch1 = (s1 + 3) >> 2;
-  int ch = (s0 >> 2) + threadIdx.x;
-  for (; ch + 3 * NT < ch1; ch += 4 * NT) {
-    Chunk c0_, c1_, c2_, c3_;
-    load_chunk<HASVAL>(a, c0, ch, c0_);
-    load_chunk<HASVAL>(a, c0, ch + NT, c1_);
-    load_chunk<HASVAL>(a, c0, ch + 2 * NT, c2_);
-    load_chunk<HASVAL>(a, c0, ch + 3 * NT, c3_);
-    axpy_chunk_r<HASVAL, true>(c0_, ch * 4, s0, s1, d, yh);
-    axpy_chunk_r<HASVAL, true>(c1_, (ch + NT) * 4, s0, s1, d, yh);
-    axpy_chunk_r<HASVAL, true>(c2_, (ch + 2 * NT) * 4, s0, s1, d, yh);
-    axpy_chunk_r<HASVAL, true>(c3_, (ch + 3 * NT) * 4, s0, s1, d, yh);
-  }
-  for (; ch < ch1; ch += NT) {
-    Chunk c;
-    load_chunk<HASVAL>(a, c0, ch, c);
-    axpy_chunk_r<HASVAL, true>(c, ch * 4, s0, s1, d, yh);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t *ix = a.colind + c0;
+  const float *vv = HASVAL ? a.colval + c0 : nullptr;
+  const int e_begin = s0 & ~127;
+  for (int e0 = e_begin + warp * 128; e0 < s1; e0 += (NT / 32) * 128) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int e = e0 + lane + 32 * k;
+      if (e >= s0 && e < s1) {
+        const int u = __ldg(ix + e);
+        atomicAdd(yh + u, HASVAL ? d * (double)__ldg(vv + e) : d);
+      }
+    }
   }
 }
 
@@ -1804,6 +1875,18 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
         int tot = staged ? nch : 0;
 #pragma unroll
         for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        {  // flattened list of the kBigBlk-entry blocks of the big slots (ascending slot order)
+          const bool big = (bmask >> lane) & 1u;
+          const int nblk = big ? ((R.sp1 + kBigBlk - 1) >> kBigShift) - (R.sp0 >> kBigShift) : 0;
+          int pb = nblk;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, pb, o);
+            if (lane >= o) pb += up;
+          }
+          T.bigpre[lane] = pb - nblk;
+          if (lane == 31) T.bigtot = pb;
+        }
         if (lane == 0) {
           T.mask = mask;
           T.bigmask = bmask;
@@ -1929,27 +2012,50 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
               }
             }
             SLIM_TICK(6);
-            for (unsigned mm = T.bigmask; mm; mm &= mm - 1) {
-              const int b = __ffs(mm) - 1;
-              const int s0 = T.rec[b].x, s1 = T.rec[b].y;
-              {
-                double v = block_dot<HASVAL>(a, T.c0[b], s0, s1, yh);
+            // big slots: their kBigBlk-entry blocks form ONE flattened list that the consumer warps stride over,
+            // so the loads of different columns overlap and no barrier is paid per column; a warp flushes
+            // its partial sum when it moves on to the next column
+            if (warp < NCW && T.bigtot > 0) {
+              ps.pwb[warp][lane] = 0.0;
+              __syncwarp();
+              unsigned mm = T.bigmask;
+              int b = __ffs(mm) - 1;
+              int pre = T.bigpre[b];
+              int4 rc = T.rec[b];
+              int nblk = ((rc.y + kBigBlk - 1) >> kBigShift) - (rc.x >> kBigShift);
+              double acc = 0.0;
+              for (int g = warp; g < T.bigtot; g += NCW) {
+                if (g >= pre + nblk) {  // next column(s): flush the finished one
 #pragma unroll
-                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) ps.pw[warp] = v;
-                __syncthreads();
-                if (tid == 0) {
-                  double sum = 0.0;
-#pragma unroll
-                  for (int i = 0; i < NW; i++) sum += ps.pw[i];
-                  ps.pcta[xb][b] = sum;
+                  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                  if (lane == 0) ps.pwb[warp][b] = acc;
+                  acc = 0.0;
+                  do {
+                    mm &= mm - 1;
+                    b = __ffs(mm) - 1;
+                    pre = T.bigpre[b];
+                    rc = T.rec[b];
+                    nblk = ((rc.y + kBigBlk - 1) >> kBigShift) - (rc.x >> kBigShift);
+                  } while (g >= pre + nblk);
                 }
-                __syncthreads();
+                acc += warp_bigblock_dot<HASVAL>(a, T.c0[b], rc.x, rc.y, (rc.x & ~(kBigBlk - 1)) + (g - pre) * kBigBlk, yh);
               }
+#pragma unroll
+              for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+              if (lane == 0) ps.pwb[warp][b] = acc;
             }
           }
           SLIM_TICK(7);
           __syncthreads();
+          if (T.bigtot > 0) {
+            if (tid < 32 && ((T.bigmask >> tid) & 1u)) {
+              double sum = 0.0;
+#pragma unroll
+              for (int w = 0; w < NCW; w++) sum += ps.pwb[w][tid];
+              ps.pcta[xb][tid] = sum;
+            }
+            __syncthreads();
+          }
           SLIM_TICK(1);
           // next round's columns + Gram block (tables are one round ahead).  Issued AFTER the barrier: a CTA
           // barrier waits for the CTA's bulk copies in flight, so they are given the exchange + solve phase
@@ -2046,10 +2152,24 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
               }
             }
           }
-          for (unsigned mm = T.bigmask; mm; mm &= mm - 1) {
-            const int b = __ffs(mm) - 1;
-            const double d = ps.dlt[b];
-            if (d != 0.0) block_axpy<HASVAL>(a, T.c0[b], T.rec[b].x, T.rec[b].y, d, yh);
+          if (warp < NCW && T.bigtot > 0) {
+            unsigned mm = T.bigmask;
+            int b = __ffs(mm) - 1;
+            int pre = T.bigpre[b];
+            int4 rc = T.rec[b];
+            int nblk = ((rc.y + kBigBlk - 1) >> kBigShift) - (rc.x >> kBigShift);
+            double d = ps.dlt[b];
+            for (int g = warp; g < T.bigtot; g += NCW) {
+              while (g >= pre + nblk) {
+                mm &= mm - 1;
+                b = __ffs(mm) - 1;
+                pre = T.bigpre[b];
+                rc = T.rec[b];
+                nblk = ((rc.y + kBigBlk - 1) >> kBigShift) - (rc.x >> kBigShift);
+                d = ps.dlt[b];
+              }
+              if (d != 0.0) warp_bigblock_axpy<HASVAL>(a, T.c0[b], rc.x, rc.y, (rc.x & ~(kBigBlk - 1)) + (g - pre) * kBigBlk, d, yh);
+            }
           }
           SLIM_TICK(10);
           if (warp == NW - 1) tab_store(r + 2, treg);  // ... consumed here, a whole round later
