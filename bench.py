@@ -45,6 +45,7 @@ WORKLOADS = {
     # name: (nusers, nitems, per_user)
     "c4": (1_000_000, 100_000, 100),   # BASELINE.json configs[3]  (metric's configuration)
     "c3": (1_000_000, 50_000, 50),     # BASELINE.json configs[2]
+    "c5": (5_000_000, 500_000, 100),   # BASELINE.json configs[4]  (8-GPU configuration; not a default bench line)
     "probe": (20_000, 2_000, 50),      # SURVEY.md section 6 probe (quick checks)
 }
 PARAMS = dict(l1r=1.0, l2r=1.0, optTol=1e-7, niters=50)

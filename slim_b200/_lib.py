@@ -7,7 +7,9 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libslim.so"
+import os
+
+LIB_PATH = Path(os.environ.get("SLIMB200_LIBRARY") or (Path(__file__).resolve().parent / "lib" / "libslim.so"))
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)

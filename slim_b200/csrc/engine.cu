@@ -1243,7 +1243,10 @@ __device__ __forceinline__ void axpy_chunk_r(const Chunk &r, int e0, int lo, int
 #define SLIM_CLUSTER_NT 256
 #endif
 constexpr int kClusterNT = SLIM_CLUSTER_NT;                 // threads per CTA of the cluster kernel
-constexpr int kClusterCtasPerSm = kClusterNT <= 256 ? 2 : 1;  // two co-resident CTAs interleave their rounds
+#ifndef SLIM_CTAS_PER_SM
+#define SLIM_CTAS_PER_SM (SLIM_CLUSTER_NT <= 256 ? 2 : 1)
+#endif
+constexpr int kClusterCtasPerSm = SLIM_CTAS_PER_SM;  // two co-resident CTAs interleave their rounds
 constexpr int kWarpSlots = 5;  // small columns of a round per consumer warp: ceil(32 / (kClusterNT/32 - 1))
 
 constexpr int kSmallCol = 1024;  // entries of a column inside one CTA's user range handled by ONE warp
@@ -2137,7 +2140,11 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
           dltx += ps.dl;
 
           // update this CTA's yhat slice: yhat += sum_k d_k a_k  (fp64 atomics: columns may share users)
+#ifdef SLIM_EXP_NOUPD
+          if (false) {
+#else
           if (warp < NCW) {
+#endif
 #pragma unroll
             for (int k = 0; k < kWarpSlots; k++) {
               const int b = T.wslot[warp][k];
@@ -2649,7 +2656,9 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       // keep the yhat vectors of all clusters in flight inside L2 (default budget 96 MB of 126 MB)
       const size_t l2_budget = (size_t)env_int("SLIMB200_L2_MB", 96) << 20;
       const int by_l2 = (int)std::max<size_t>(1, l2_budget / (row_stride * sizeof(double)));
-      nclusters = std::min(hw, by_l2);
+      // ... but never fewer than 8 clusters: with very many users (C5: 40 MB per yhat) part of the gathers
+      // then comes from HBM, which still beats leaving most SMs idle
+      nclusters = std::min(hw, std::max(by_l2, 8));
       if (env_int("SLIMB200_NCLUSTERS", 0) > 0) nclusters = env_int("SLIMB200_NCLUSTERS", 0);
       nclusters = std::max(1, std::min(std::min(nclusters, hw), std::max(nsel, 1)));
       plan.grid = nclusters * cs;
