@@ -1948,6 +1948,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
           double xi = 0.0;
           if (warp == 0 && ((mask >> lane) & 1u)) xi = x[T.rec[lane].w];  // consumed by the solve
           if (warp == NW - 1) {
+            issue_copies(r + 1, buf ^ 1u);  // next round's columns + Gram block: a full round to land
             tab_load(gm_ahead, treg);       // start reading the coordinate lines of round r + 2 ...
             gm_ahead = group_rec(r + 3);    // ... and the window record of round r + 3
           }
@@ -2060,10 +2061,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
             __syncthreads();
           }
           SLIM_TICK(1);
-          // next round's columns + Gram block (tables are one round ahead).  Issued AFTER the barrier: a CTA
-          // barrier waits for the CTA's bulk copies in flight, so they are given the exchange + solve phase
-          // to land instead of stalling the barrier above.
-          if (warp == NW - 1) issue_copies(r + 1, buf ^ 1u);
+
           {
             // all-gather of the 32 partials across the cluster: warp w stores this CTA's 32 values, each
             // tagged with the round number, into CTA w's pall[xb][rank][.] (coalesced DSMEM stores)
