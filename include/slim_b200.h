@@ -49,6 +49,14 @@ int32_t SLIMB200_MatrixItemOrder(const slimb200_matrix_t *matrix, int32_t *rank)
  * <a_k, a_m> for the items with INTERNAL ids 32w+k and 32w+m (zero diagonal). */
 int32_t SLIMB200_MatrixWindowGram(const slimb200_matrix_t *matrix, double *out);
 
+/* Gram matrix G = R^T R (internal item order) that staging builds for the Gram-space solver when it fits in
+ * HBM: every <a_i, a_k> the coordinate-descent sweeps of cd.c:117-133 need.  elem_bytes = 0 (not staged:
+ * too large, or SLIMB200_GRAM=0), 4 (float, exact: integer ratings and sums below 2^24) or 8 (double);
+ * build_ms = CUDA-event time of the build.  SLIMB200_MatrixGram copies it back densely, ncols x ncols
+ * elements of that type without row padding (tests). */
+int32_t SLIMB200_MatrixGramInfo(const slimb200_matrix_t *matrix, int32_t *elem_bytes, double *build_ms);
+int32_t SLIMB200_MatrixGram(const slimb200_matrix_t *matrix, void *out);
+
 /* Solve target columns cols[0..ncols_sel) (cols == NULL: every column): the per-column body of
  * EstimateModelCD (reference src/libslim/estimate.c:405-505) + CoordinateDescent (cd.c:101-142).
  * Options as for SLIM_Learn.  imodel: optional warm-start model handle. */

@@ -346,6 +346,21 @@ class Staged:
         assert rc == SLIM_OK
         return out[:nwin]
 
+    def gram_info(self):
+        """(element bytes, build ms) of the staged Gram matrix R^T R; element bytes 0 = not staged."""
+        eb, ms = C.c_int32(0), C.c_double(0.0)
+        assert self._lib.SLIMB200_MatrixGramInfo(self.handle, C.byref(eb), C.byref(ms)) == SLIM_OK
+        return eb.value, ms.value
+
+    def gram(self):
+        """Dense copy of the staged Gram matrix (internal item order), None when it was not staged."""
+        eb, _ = self.gram_info()
+        if eb == 0:
+            return None
+        out = np.zeros((self.ncols, self.ncols), np.float32 if eb == 4 else np.float64)
+        assert self._lib.SLIMB200_MatrixGram(self.handle, out.ctypes.data_as(C.c_void_p)) == SLIM_OK
+        return out
+
     def close(self):
         if getattr(self, "handle", None):
             h = C.c_void_p(self.handle)

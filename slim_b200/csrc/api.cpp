@@ -746,6 +746,17 @@ int32_t SLIMB200_MatrixWindowGram(const slimb200_matrix_t *matrix, double *out) 
   return matrix_window_gram_to_host(reinterpret_cast<const Matrix *>(matrix), out);
 }
 
+int32_t SLIMB200_MatrixGramInfo(const slimb200_matrix_t *matrix, int32_t *elem_bytes, double *build_ms) {
+  if (!matrix) return SLIM_ERROR_INPUT;
+  matrix_gram_info(reinterpret_cast<const Matrix *>(matrix), elem_bytes, build_ms);
+  return SLIM_OK;
+}
+
+int32_t SLIMB200_MatrixGram(const slimb200_matrix_t *matrix, void *out) {
+  if (!matrix || !out) return SLIM_ERROR_INPUT;
+  return matrix_gram_to_host(reinterpret_cast<const Matrix *>(matrix), out);
+}
+
 slimb200_result_t *SLIMB200_LearnColumns(slimb200_matrix_t *matrix, const int32_t *ioptions, const double *doptions,
                                          const int32_t *cols, int32_t ncols_sel, const slim_t *imodel,
                                          int32_t *r_status) {

@@ -133,7 +133,14 @@ struct Matrix {
   float *d_cnorms = nullptr;
   double *d_csq = nullptr;
   std::vector<int32_t> h_colcnt;
+  // Gram matrix G = R^T R in internal item order (gram.cuh): the Gram-space solver reads rows of it
+  void *d_gram = nullptr;          // float[ncols][gram_ld] (exact integer sums) or double[ncols][gram_ld]
+  size_t gram_ld = 0;
+  bool gram_f64 = false;
+  unsigned long long *d_expand = nullptr;  // per item: sum of len(row_u) over the users of the column
+  double gram_ms = 0.0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second stream: light and heavy Gram launches run side by side
   int sm_count = 0;
   int smem_optin = 0;
   double stage_ms = 0.0;
@@ -160,6 +167,9 @@ void free_matrix(Matrix *m) {
   cudaFree(m->d_rank);
   cudaFree(m->d_inv);
   cudaFree(m->d_scratch);
+  cudaFree(m->d_gram);
+  cudaFree(m->d_expand);
+  if (m->stream2) cudaStreamDestroy(m->stream2);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -442,6 +452,8 @@ static int grid_for(int64_t n, int block, int sm_count) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm_count * 16));
 }
 
+static void build_gram(Matrix *m);  // defined next to the Gram kernels (gram.cuh)
+
 Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *rowind,
               const float *rowval, bool on_device, int64_t nnz_if_device, int32_t *status) {
   Matrix *m = nullptr;
@@ -458,6 +470,7 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
     m->sm_count = prop.multiProcessorCount;
     m->smem_optin = (int)prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     cudaStream_t s = m->stream;
     m->nrows = nrows;
     m->nnz = on_device ? nnz_if_device : (int64_t)rowptr[nrows];
@@ -665,6 +678,7 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(s));  // staging buffers are released at scope exit
     }
+    build_gram(m);
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, s));
     CK(cudaStreamSynchronize(s));
@@ -696,6 +710,25 @@ int matrix_window_gram_to_host(const Matrix *m, double *out) {
     DeviceGuard guard(m->device);
     const size_t n = (size_t)((m->ncols + 31) / 32) * 1024;
     if (n > 0) CK(cudaMemcpy(out, m->d_wgram, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return kOk;
+  } catch (const EngineError &e) {
+    g_last_error = e.what();
+    return e.status;
+  }
+}
+
+void matrix_gram_info(const Matrix *m, int32_t *elem_bytes, double *build_ms) {
+  if (elem_bytes) *elem_bytes = m->d_gram ? (m->gram_f64 ? 8 : 4) : 0;
+  if (build_ms) *build_ms = m->gram_ms;
+}
+
+int matrix_gram_to_host(const Matrix *m, void *out) {
+  try {
+    if (!m->d_gram) throw EngineError(kErrInput, "matrix_gram_to_host: no Gram matrix was staged");
+    DeviceGuard guard(m->device);
+    const size_t esz = m->gram_f64 ? 8 : 4;
+    CK(cudaMemcpy2D(out, (size_t)m->ncols * esz, m->d_gram, m->gram_ld * esz, (size_t)m->ncols * esz,
+                    (size_t)m->ncols, cudaMemcpyDeviceToHost));
     return kOk;
   } catch (const EngineError &e) {
     g_last_error = e.what();
@@ -2377,6 +2410,115 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
   }
 }
 
+#include "gram.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// K0g host side: decide whether G fits, pick its element type, build it (part of staging).
+//   SLIMB200_GRAM=0        never build G (the user-space kernels are used)
+//   SLIMB200_GRAM_GB=n     upper bound for G in GiB (default 100); G must also fit the free memory
+//   SLIMB200_GRAM_F64=1    force double elements
+// ------------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt);
+
+static void build_gram(Matrix *m) {
+  const int32_t ncols = m->ncols;
+  if (ncols <= 0 || m->nnz <= 0 || !env_int("SLIMB200_GRAM", 1)) return;
+  cudaStream_t s = m->stream;
+  // element type: fp32 sums are exact iff the ratings are integers and no sum can reach 2^24
+  bool exact32 = true;
+  const bool kv = m->has_val && !m->unit;
+  if (kv) {
+    DevBuf<int32_t> d_flag;
+    d_flag.alloc_zero(1, s);
+    integer_values_kernel<<<grid_for(m->nnz, 256, m->sm_count), 256, 0, s>>>(m->d_rowval, m->nnz, d_flag.p);
+    m->stage_launches++;
+    int32_t flag = 1;
+    CK(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    exact32 = flag == 0;
+  }
+  if (exact32) {
+    std::vector<double> csq(ncols);
+    CK(cudaMemcpyAsync(csq.data(), m->d_csq, sizeof(double) * ncols, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    double mx = 0.0;
+    for (double v : csq) mx = std::max(mx, v);
+    exact32 = mx < 16777216.0;  // |G[i][k]| <= sqrt(csq_i csq_k) <= max csq (Cauchy-Schwarz), also every partial sum
+  }
+  if (env_int("SLIMB200_GRAM_F64", 0)) exact32 = false;
+  const size_t esz = exact32 ? sizeof(float) : sizeof(double);
+  const size_t ld = ((size_t)ncols + 31) & ~size_t(31);
+  const size_t bytes = (size_t)ncols * ld * esz;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = (size_t)env_int("SLIMB200_GRAM_GB", 100) << 30;
+  // leave room for the solve scratch and the result pools
+  const size_t reserve = (size_t)16 << 30;
+  if (bytes > budget || bytes + std::min(reserve, total_b / 4) > free_b) {
+    if (env_int("SLIMB200_VERBOSE", 0))
+      fprintf(stderr, "[slim-b200] Gram matrix (%.1f GB) does not fit: user-space kernels will be used\n", bytes / 1e9);
+    return;
+  }
+  cudaEvent_t g0, g1;
+  CK(cudaEventCreate(&g0));
+  CK(cudaEventCreate(&g1));
+  CK(cudaEventRecord(g0, s));
+  if (cudaMalloc(&m->d_gram, bytes) != cudaSuccess) {  // not fatal: fall back to the user-space kernels
+    (void)cudaGetLastError();
+    m->d_gram = nullptr;
+    cudaEventDestroy(g0);
+    cudaEventDestroy(g1);
+    return;
+  }
+  CK(cudaMemsetAsync(m->d_gram, 0, bytes, s));
+  CK(cudaMalloc(&m->d_expand, sizeof(unsigned long long) * ncols));
+  CK(cudaMemsetAsync(m->d_expand, 0, sizeof(unsigned long long) * ncols, s));
+  m->gram_ld = ld;
+  m->gram_f64 = !exact32;
+  // work items (column, entry range), heaviest columns first (internal ids are in popularity order)
+  constexpr int32_t kSeg = 2048;
+  std::vector<int32_t> wc, w0, w1;
+  for (int32_t k = 0; k < ncols; k++)
+    for (int32_t e = 0; e < m->h_colcnt[k]; e += kSeg) {
+      wc.push_back(k);
+      w0.push_back(e);
+      w1.push_back(std::min(m->h_colcnt[k], e + kSeg));
+    }
+  const int32_t nwork = (int32_t)wc.size();
+  DevBuf<int32_t> d_wc, d_w0, d_w1;
+  d_wc.alloc(nwork);
+  d_w0.alloc(nwork);
+  d_w1.alloc(nwork);
+  if (nwork > 0) {
+    CK(cudaMemcpyAsync(d_wc.p, wc.data(), sizeof(int32_t) * nwork, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_w0.p, w0.data(), sizeof(int32_t) * nwork, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_w1.p, w1.data(), sizeof(int32_t) * nwork, cudaMemcpyHostToDevice, s));
+    const int grid = std::max(1, std::min(nwork, m->sm_count * 8));
+#define SLIM_GRAM_BUILD(GT, HV)                                                                              \
+  gram_build_kernel<GT, HV><<<grid, 256, 0, s>>>(nwork, d_wc.p, d_w0.p, d_w1.p, m->d_colptr, m->d_colind,      \
+                                                 m->d_colval, m->d_rowptr, m->d_rowind, m->d_rowval,         \
+                                                 static_cast<GT *>(m->d_gram), ld, m->d_expand)
+    if (exact32) {
+      if (kv) SLIM_GRAM_BUILD(float, true); else SLIM_GRAM_BUILD(float, false);
+    } else {
+      if (kv) SLIM_GRAM_BUILD(double, true); else SLIM_GRAM_BUILD(double, false);
+    }
+#undef SLIM_GRAM_BUILD
+    CK(cudaGetLastError());
+    m->stage_launches++;
+  }
+  CK(cudaEventRecord(g1, s));
+  CK(cudaStreamSynchronize(s));  // the work list is released at scope exit
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, g0, g1));
+  m->gram_ms = ms;
+  cudaEventDestroy(g0);
+  cudaEventDestroy(g1);
+  if (env_int("SLIMB200_VERBOSE", 0))
+    fprintf(stderr, "[slim-b200] Gram matrix: %d x %zu %s, %.2f GB, %d work items, built in %.1f ms\n", ncols, ld,
+            exact32 ? "fp32 (exact)" : "fp64", bytes / 1e9, nwork, ms);
+}
+
 // K3 (second half): ordered gather of the solved columns into compact CSC arrays (the CSC
 // assembly of SaveModel, estimate.c:570-588).  One warp per column.
 constexpr int kMaxPools = 10;
@@ -2572,6 +2714,49 @@ static int cluster_dispatch(bool vals, bool window, const SolveArgs &args, const
                 : cluster_launch<false, false>(args, cargs, cs, nclusters, s, query_only);
 }
 
+// Launch (or, with query_only, size) cd_gram_kernel<GT, CS>.  Query: CTAs per SM for CS == 1, co-resident
+// clusters on the device for CS > 1.  `count` = CTAs (CS == 1) or clusters (CS > 1) to launch.
+template <typename GT, int CS>
+static int gram_launch_t(const SolveArgs &args, const GramArgs &gargs, int count, cudaStream_t s, bool query_only) {
+  auto kern = cd_gram_kernel<GT, CS>;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)(CS * std::max(count, 1)), 1, 1);
+  cfg.blockDim = dim3(kGramNT, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = CS > 1 ? 1 : 0;
+  if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  if (query_only) {
+    int n = 0;
+    if (CS == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kGramNT, 0));
+    else CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    return n;
+  }
+  CK(cudaLaunchKernelEx(&cfg, kern, args, gargs));
+  return 0;
+}
+
+static int gram_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &gargs, int count, cudaStream_t s,
+                       bool query_only) {
+#define SLIM_GRAM_CS(CSV)                                                                        \
+  if (cs == CSV)                                                                                 \
+    return f64 ? gram_launch_t<double, CSV>(args, gargs, count, s, query_only)                   \
+               : gram_launch_t<float, CSV>(args, gargs, count, s, query_only);
+  SLIM_GRAM_CS(1)
+  SLIM_GRAM_CS(2)
+  SLIM_GRAM_CS(4)
+  SLIM_GRAM_CS(8)
+  SLIM_GRAM_CS(16)
+#undef SLIM_GRAM_CS
+  throw EngineError(kErr, "gram_launch: unsupported cluster size");
+}
+
 static size_t smem_for(int nt, bool ysmem, int32_t nrows) {
   size_t fixed = nt == 32 ? solve_fixed_smem<32>() : nt == 128 ? solve_fixed_smem<128>() : solve_fixed_smem<512>();
   fixed = (fixed + 15) & ~size_t(15);
@@ -2618,6 +2803,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     });
 
     // ---- launch plan ---------------------------------------------------------------------------
+    // Gram-space solver whenever G was staged (gram.cuh); otherwise the user-space kernels below
+    const bool use_gram = m->d_gram != nullptr && env_int("SLIMB200_GRAM", 1) != 0;
     const bool kernel_vals = m->has_val && !m->unit;
     LaunchPlan plan{};
     const double mean_col = ncols > 0 ? (double)m->nnz / ncols : 0.0;
@@ -2643,6 +2830,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     // yhat too large for shared memory: thread-block clusters with yhat resident in L2
     int cs = env_int("SLIMB200_CLUSTER", plan.ysmem ? 0 : 16);
     if (cs != 0 && cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) cs = 16;
+    if (use_gram) cs = 0;
     const bool use_cluster = cs > 0;
     const bool use_window = use_cluster && env_int("SLIMB200_WINDOW", 1) != 0;
     const size_t col_stride = ((size_t)std::max(ncols, 1) + 3) & ~size_t(3);
@@ -2664,7 +2852,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         fprintf(stderr, "[slim-b200] cluster kernel: cluster=%d CTAs x %d threads, %d clusters in flight (hw max %d, "
                         "L2 budget allows %d), values=%d, window sweep=%d\n", cs, kClusterNT, nclusters, hw, by_l2,
                 (int)kernel_vals, (int)use_window);
-    } else {
+    } else if (!use_gram) {
       int bps = 1;
       dispatch_solve(args, plan, kernel_vals, s, true, &bps);
       bps = std::max(1, bps);
@@ -2675,6 +2863,27 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
                 plan.nt, plan.ysmem ? "smem" : "global", plan.grid, bps, (int)kernel_vals);
     }
 
+    // Gram-space plan: targets with at least gram_heavy nonzeros go to clusters of gram_cs CTAs, the rest
+    // to single CTAs; the two launches run side by side on two streams.
+    GramArgs gargs{};
+    int gram_cs = env_int("SLIMB200_GRAM_CS", 8);
+    if (gram_cs != 1 && gram_cs != 2 && gram_cs != 4 && gram_cs != 8 && gram_cs != 16) gram_cs = 8;
+    const int gram_heavy = env_int("SLIMB200_GRAM_HEAVY", 1500);
+    int gram_grid_light = 0, gram_clusters = 0;
+    if (use_gram) {
+      gram_grid_light = gram_launch(m->gram_f64, 1, args, gargs, 1, s, true) * m->sm_count;
+      gram_clusters = gram_cs > 1 ? gram_launch(m->gram_f64, gram_cs, args, gargs, 1, s, true) : 0;
+      if (gram_grid_light < 1 || (gram_cs > 1 && gram_clusters < 1))
+        throw EngineError(kErr, "learn: Gram kernel launch configuration not supported on this device");
+      gram_grid_light = std::min(gram_grid_light, std::max(nsel, 1));
+      gram_clusters = std::min(gram_clusters, std::max(nsel, 1));
+      if (env_int("SLIMB200_GRAM_CLUSTERS", 0) > 0) gram_clusters = std::min(gram_clusters, env_int("SLIMB200_GRAM_CLUSTERS", 0));
+      plan.grid = gram_grid_light + gram_clusters * gram_cs;
+      if (env_int("SLIMB200_VERBOSE", 0))
+        fprintf(stderr, "[slim-b200] Gram-space kernel (%s G): %d single CTAs + %d clusters of %d CTAs, heavy >= %d nnz\n",
+                m->gram_f64 ? "fp64" : "fp32", gram_grid_light, gram_clusters, gram_cs, gram_heavy);
+    }
+
     // ---- scratch (cached on the matrix) --------------------------------------------------------
     const size_t g = use_cluster ? (size_t)nclusters : (size_t)plan.grid;  // scratch slots
     size_t off = 0;
@@ -2683,13 +2892,16 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       off += (bytes + 255) & ~size_t(255);
       return o;
     };
-    const size_t o_acc = carve(g * col_stride * sizeof(double));
+    const size_t o_acc = carve(use_gram ? 0 : g * col_stride * sizeof(double));
     const size_t o_xw = carve(g * col_stride * sizeof(float));
-    const size_t o_yh = carve((plan.ysmem && !use_cluster) ? 0 : g * row_stride * sizeof(double));
+    const size_t o_yh = carve(((plan.ysmem && !use_cluster) || use_gram) ? 0 : g * row_stride * sizeof(double));
     const size_t zero_bytes = off;  // acc, xw, yhat must start at zero
-    const size_t o_meta = carve(g * col_stride * (use_cluster ? sizeof(ActMetaC) : sizeof(ActMeta)));
+    const size_t o_meta = carve(use_gram ? 0 : g * col_stride * (use_cluster ? sizeof(ActMetaC) : sizeof(ActMeta)));
     const size_t o_x = carve((use_cluster ? (size_t)plan.grid : g) * col_stride * sizeof(double));
     const size_t o_idx = carve(g * col_stride * sizeof(int32_t));
+    const size_t o_gslot = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
+    const size_t o_grow = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
+    const size_t o_gval = carve(use_gram ? g * col_stride * sizeof(double) : 0);
     const size_t grp_stride = (size_t)(ncols + 31) / 32 + 1;
     const size_t o_grp = carve(use_cluster ? g * grp_stride * sizeof(GroupMeta) : 0);
     if (off > m->scratch_bytes) {
@@ -2754,6 +2966,16 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     cargs.groups = reinterpret_cast<GroupMeta *>(sb + o_grp);
     cargs.grp_stride = grp_stride;
     args.act_idx = reinterpret_cast<int32_t *>(sb + o_idx);
+    if (use_gram) {
+      gargs.G = m->d_gram;
+      gargs.ld = m->gram_ld;
+      gargs.act = reinterpret_cast<int32_t *>(sb + o_idx);
+      gargs.x = reinterpret_cast<double *>(sb + o_x);
+      gargs.slotp = reinterpret_cast<int32_t *>(sb + o_gslot);
+      gargs.sl_row = reinterpret_cast<int32_t *>(sb + o_grow);
+      gargs.sl_val = reinterpret_cast<double *>(sb + o_gval);
+      gargs.expand = m->d_expand;
+    }
     args.col_stride = col_stride;
     args.row_stride = row_stride;
 
@@ -2794,7 +3016,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         DevBuf<int32_t> d_ng;
         DevBuf<unsigned long long> d_used;
         d_targets.alloc(nt);
-        d_queue.alloc_zero(1, s);
+        d_queue.alloc_zero(2, s);
         d_used.alloc_zero(1, s);
         d_ocnt.alloc(nt);
         d_ooff.alloc(nt);
@@ -2831,7 +3053,41 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         LaunchPlan lp = plan;
         lp.grid = std::min(plan.grid, nt);
         CK(cudaEventRecord(e0, s));
-        if (use_cluster) {
+        if (use_gram) {
+          // `pending` is sorted by descending column nnz: the heavy targets are a prefix
+          int32_t nheavy = 0;
+          if (gram_cs > 1)
+            while (nheavy < nt && m->h_colcnt[tcols[nheavy]] >= gram_heavy) nheavy++;
+          const int32_t nlight = nt - nheavy;
+          cudaStream_t s2 = m->stream2;
+          if (nheavy > 0 && nlight > 0) {
+            CK(cudaEventRecord(e2, s));
+            CK(cudaStreamWaitEvent(s2, e2, 0));
+          }
+          if (nheavy > 0) {
+            GramArgs gh = gargs;
+            gh.q_begin = 0;
+            gh.q_end = nheavy;
+            gh.queue = d_queue.p;
+            gh.slot_base = 0;
+            gram_launch(m->gram_f64, gram_cs, args, gh, std::min(gram_clusters, nheavy), s, false);
+          }
+          if (nlight > 0) {
+            GramArgs gl = gargs;
+            gl.q_begin = nheavy;
+            gl.q_end = nt;
+            gl.queue = d_queue.p + 1;
+            gl.slot_base = gram_clusters * gram_cs;
+            gram_launch(m->gram_f64, 1, args, gl, std::min(gram_grid_light, nlight), nheavy > 0 ? s2 : s, false);
+            if (nheavy > 0) {
+              CK(cudaEventRecord(e2, s2));
+              CK(cudaStreamWaitEvent(s, e2, 0));
+              res->tm.launches++;  // two solve launches in this round (the common accounting adds one)
+              res->tm.solve_launches++;
+            }
+          }
+          CK(cudaGetLastError());
+        } else if (use_cluster) {
           const int ncl = std::min(nclusters, nt);
           cluster_dispatch(kernel_vals, use_window, args, cargs, cs, ncl, s, false);
           CK(cudaGetLastError());

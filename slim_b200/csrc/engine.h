@@ -51,6 +51,12 @@ int matrix_item_order_to_host(const Matrix *m, int32_t *rank);
 // Window Gram blocks in INTERNAL item order (tests): double[ceil(ncols/32)][32][32].
 int matrix_window_gram_to_host(const Matrix *m, double *out);
 
+// Gram matrix G = R^T R staged for the Gram-space solver (INTERNAL item order).  elem_bytes: 0 when G
+// was not staged (too large / disabled), 4 = float (exact integer sums), 8 = double.
+void matrix_gram_info(const Matrix *m, int32_t *elem_bytes, double *build_ms);
+// Dense ncols x ncols copy (no row padding) in the element type reported above (tests).
+int matrix_gram_to_host(const Matrix *m, void *out);
+
 Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel,
               const WarmStart *warm, int32_t *status);
 void free_result(Result *r);

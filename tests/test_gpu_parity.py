@@ -158,6 +158,7 @@ def test_default_setting_matches_oracle_same_order(lib, ours, oracle, name):
 @pytest.mark.parametrize("yglobal", ["0", "1"])
 @pytest.mark.parametrize("ratings,null_vals", [(False, False), (True, False), (False, True)])
 def test_kernel_variants_small(lib, ours, oracle, monkeypatch, nt, yglobal, ratings, null_vals):
+    monkeypatch.setenv("SLIMB200_GRAM", "0")  # the user-space team kernel
     monkeypatch.setenv("SLIMB200_NT", nt)
     monkeypatch.setenv("SLIMB200_YHAT_GLOBAL", yglobal)
     rp, ri, rv = st.synth_zipf(700, 260, 24, seed=13, ratings=ratings)
@@ -177,6 +178,7 @@ def test_cluster_kernel_variants(lib, ours, oracle, monkeypatch, cs, window, rat
     # the thread-block-cluster kernel (used when yhat does not fit shared memory), forced on a small R;
     # window=1: 32-coordinate exact block updates through the staged Gram blocks, window=0: one
     # coordinate per cluster barrier
+    monkeypatch.setenv("SLIMB200_GRAM", "0")  # the user-space kernels
     monkeypatch.setenv("SLIMB200_CLUSTER", cs)
     monkeypatch.setenv("SLIMB200_WINDOW", window)
     rp, ri, rv = st.synth_zipf(1000, 260, 24, seed=29, ratings=ratings)
@@ -192,6 +194,7 @@ def test_cluster_kernel_variants(lib, ours, oracle, monkeypatch, cs, window, rat
 @pytest.mark.parametrize("cs", ["0", "16"])
 def test_unit_values_take_the_index_only_path(lib, ours, monkeypatch, cs):
     # all-ones ratings: dropping the value stream on the device must not change a single bit
+    monkeypatch.setenv("SLIMB200_GRAM", "0")  # the user-space kernels
     monkeypatch.setenv("SLIMB200_CLUSTER", cs)
     rp, ri, rv = st.synth_zipf(3000, 300, 30, seed=31)
     h0 = _learn(ours, rp, ri, rv, niters=50)
@@ -206,6 +209,7 @@ def test_unit_values_take_the_index_only_path(lib, ours, monkeypatch, cs):
 
 @pytest.mark.parametrize("cs,window", [("0", "1"), ("8", "0"), ("8", "1"), ("16", "1"), ("2", "1")])
 def test_long_columns_and_iteration_cap(lib, ours, oracle, monkeypatch, cs, window):
+    monkeypatch.setenv("SLIMB200_GRAM", "0")  # the user-space kernels
     monkeypatch.setenv("SLIMB200_CLUSTER", cs)
     monkeypatch.setenv("SLIMB200_WINDOW", window)
     # dense head columns (nnz ~ nusers) exercise the multi-chunk path; niters=50 caps head targets
@@ -228,6 +232,7 @@ def test_long_columns_and_iteration_cap(lib, ours, oracle, monkeypatch, cs, wind
 
 @pytest.mark.parametrize("cs", ["0", "16"])
 def test_warm_start(lib, ours, oracle, monkeypatch, cs):
+    monkeypatch.setenv("SLIMB200_GRAM", "0")  # the user-space kernels
     monkeypatch.setenv("SLIMB200_CLUSTER", cs)
     rp, ri, rv = st.synth_zipf(900, 200, 20, seed=17, ratings=True)
     h0 = _learn(ours, rp, ri, rv, l1r=3.0, l2r=1.0, niters=30)
@@ -252,6 +257,7 @@ def test_window_sweep_large_and_small_columns(lib, ours, oracle, monkeypatch):
     rp, ri, rv = st.synth_zipf(40000, 600, 30, seed=77)
     cols = np.arange(0, 600, 13, dtype=np.int32)
     ref = oracle.learn(rp, ri, rv, niters=30, cols=cols, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
+    monkeypatch.setenv("SLIMB200_GRAM", "0")  # the user-space cluster kernel
     for cs in ("1", "4", "16"):
         monkeypatch.setenv("SLIMB200_CLUSTER", cs)
         with Staged(rp, ri, rv) as s:
@@ -261,6 +267,116 @@ def test_window_sweep_large_and_small_columns(lib, ours, oracle, monkeypatch):
         assert np.array_equal(stats["nactive"], ref["stats"]["nactive"])
         _check_close(got, ref, tol=1e-6)
         assert np.allclose(stats["objval"], ref["stats"]["objval"], rtol=1e-9)
+
+
+# ---- the Gram-space solver (slim_b200/csrc/gram.cuh): the default whenever G = R^T R fits in HBM ----------
+
+def test_gram_matrix_is_exact(lib):
+    # G staged by gram_build_kernel == R^T R in the engine's internal item order, bit for bit (integer ratings)
+    import scipy.sparse as sp
+
+    from slim_b200 import Staged
+
+    for ratings in (False, True):
+        rp, ri, rv = st.synth_zipf(3000, 200, 25, seed=8, ratings=ratings)
+        R = sp.csr_matrix((rv.astype(np.float64), ri, rp), shape=(3000, 200))
+        G = (R.T @ R).toarray()
+        with Staged(rp, ri, rv) as s:
+            got = s.gram()
+            rank = s.item_order()
+        assert got is not None and got.dtype == np.float32
+        inv = np.argsort(rank)
+        assert np.array_equal(got.astype(np.float64), G[np.ix_(inv, inv)])
+
+
+@pytest.mark.parametrize("cs", ["1", "2", "4", "8", "16"])
+@pytest.mark.parametrize("heavy", ["0", "30", "1000000"])  # all targets on clusters / mixed / all on single CTAs
+@pytest.mark.parametrize("ratings,null_vals", [(False, False), (True, False), (False, True)])
+def test_gram_kernel_variants(lib, ours, oracle, monkeypatch, cs, heavy, ratings, null_vals):
+    monkeypatch.setenv("SLIMB200_GRAM_CS", cs)
+    monkeypatch.setenv("SLIMB200_GRAM_HEAVY", heavy)
+    rp, ri, rv = st.synth_zipf(1000, 260, 24, seed=29, ratings=ratings)
+    if null_vals:
+        rv = None
+    kw = dict(l1r=0.7, l2r=1.5, **CONV)
+    h = _learn(ours, rp, ri, rv, **kw)
+    w = oracle.learn(rp, ri, rv, nthreads=8, **kw, order=st.ORDER_POPULARITY)
+    _check_close(st.model_views(h), w)
+    ours.free(h)
+
+
+@pytest.mark.parametrize("cs,heavy", [("1", "0"), ("8", "0"), ("16", "200")])
+@pytest.mark.parametrize("f64", ["0", "1"])
+def test_gram_real_valued_ratings(lib, ours, oracle, monkeypatch, cs, heavy, f64):
+    # non-integer ratings: fp32 sums would not be exact, G is staged in fp64 (also forced on integer data)
+    monkeypatch.setenv("SLIMB200_GRAM_CS", cs)
+    monkeypatch.setenv("SLIMB200_GRAM_HEAVY", heavy)
+    monkeypatch.setenv("SLIMB200_GRAM_F64", f64)
+    rp, ri, rv = st.synth_zipf(1200, 240, 20, seed=19, ratings=True)
+    if f64 == "0":
+        rv = (rv * np.random.default_rng(3).uniform(0.2, 1.0, len(rv))).astype(np.float32)
+    kw = dict(l1r=0.4, l2r=1.0, **CONV)
+    h = _learn(ours, rp, ri, rv, **kw)
+    w = oracle.learn(rp, ri, rv, nthreads=8, **kw, order=st.ORDER_POPULARITY)
+    _check_close(st.model_views(h), w)
+    ours.free(h)
+
+
+@pytest.mark.parametrize("cs,heavy", [("1", "0"), ("8", "0"), ("16", "0"), ("4", "300")])
+def test_gram_long_columns_and_iteration_cap(lib, ours, oracle, monkeypatch, cs, heavy):
+    # same case as the user-space kernels: capped head targets must follow the oracle sweep by sweep
+    monkeypatch.setenv("SLIMB200_GRAM_CS", cs)
+    monkeypatch.setenv("SLIMB200_GRAM_HEAVY", heavy)
+    rp, ri, rv = st.synth_zipf(6000, 400, 40, seed=21)
+    from slim_b200 import Staged, learn_columns
+
+    cols = np.arange(0, 400, 7, dtype=np.int32)
+    with Staged(rp, ri, rv) as s:
+        assert s.gram() is not None
+        r = learn_columns(s, dict(niters=50), cols=cols)
+        got, stats = r.to_host(), r.stats()
+    ref = oracle.learn(rp, ri, rv, niters=50, cols=cols, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
+    assert np.array_equal(stats["nactive"], ref["stats"]["nactive"])
+    assert np.array_equal(stats["active_nnz"], ref["stats"]["active_nnz"])
+    assert np.array_equal(stats["expand_nnz"], ref["stats"]["expand_nnz"])
+    assert np.array_equal(stats["niters"], ref["stats"]["niters"])
+    _check_close(got, ref, tol=1e-6)
+    assert np.allclose(stats["objval"], ref["stats"]["objval"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(stats["rnorm"], ref["stats"]["rnorm"], rtol=1e-9, atol=1e-7)
+
+
+@pytest.mark.parametrize("cs,heavy", [("1", "0"), ("8", "0")])
+def test_gram_warm_start(lib, ours, oracle, monkeypatch, cs, heavy):
+    monkeypatch.setenv("SLIMB200_GRAM_CS", cs)
+    monkeypatch.setenv("SLIMB200_GRAM_HEAVY", heavy)
+    rp, ri, rv = st.synth_zipf(900, 200, 20, seed=17, ratings=True)
+    h0 = _learn(ours, rp, ri, rv, l1r=3.0, l2r=1.0, niters=30)
+    m0 = st.model_views(h0)
+    h1 = _learn(ours, rp, ri, rv, imodel=h0, l1r=1.0, l2r=1.0, niters=5)
+    w1 = oracle.learn(rp, ri, rv, l1r=1.0, l2r=1.0, niters=5, nthreads=4,
+                      imodel=(m0["ncols"], m0["colptr"], m0["colind"], m0["colval"]), order=st.ORDER_POPULARITY)
+    _check_close(st.model_views(h1), w1, tol=1e-6)
+    for h in (h0, h1):
+        ours.free(h)
+
+
+def test_gram_and_user_space_kernels_agree(lib, monkeypatch):
+    # same visiting order, same update rule: the two formulations differ by fp64 rounding only
+    from slim_b200 import Staged, learn_columns
+
+    rp, ri, rv = st.synth_zipf(40000, 600, 30, seed=77)
+    cols = np.arange(0, 600, 13, dtype=np.int32)
+    out = {}
+    for gram in ("1", "0"):
+        monkeypatch.setenv("SLIMB200_GRAM", gram)
+        with Staged(rp, ri, rv) as s:
+            r = learn_columns(s, dict(niters=30), cols=cols)
+            out[gram] = (r.to_host(), r.stats())
+    assert np.array_equal(out["1"][1]["niters"], out["0"][1]["niters"])
+    assert np.array_equal(out["1"][1]["nactive"], out["0"][1]["nactive"])
+    assert np.array_equal(out["1"][1]["expand_nnz"], out["0"][1]["expand_nnz"])
+    _check_close(out["1"][0], out["0"][0], tol=1e-6)
+    assert np.allclose(out["1"][1]["objval"], out["0"][1]["objval"], rtol=1e-9)
 
 
 def test_edge_cases(lib, ours, oracle):
