@@ -140,7 +140,8 @@ struct Matrix {
   unsigned long long *d_expand = nullptr;  // per item: sum of len(row_u) over the users of the column
   double gram_ms = 0.0;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // second stream: light and heavy Gram launches run side by side
+  cudaStream_t stream2 = nullptr;  // extra streams: the Gram launches of the target classes run side by side
+  cudaStream_t stream3 = nullptr;
   int sm_count = 0;
   int smem_optin = 0;
   double stage_ms = 0.0;
@@ -170,6 +171,7 @@ void free_matrix(Matrix *m) {
   cudaFree(m->d_gram);
   cudaFree(m->d_expand);
   if (m->stream2) cudaStreamDestroy(m->stream2);
+  if (m->stream3) cudaStreamDestroy(m->stream3);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -471,6 +473,7 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
     m->smem_optin = (int)prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&m->stream3, cudaStreamNonBlocking));
     cudaStream_t s = m->stream;
     m->nrows = nrows;
     m->nnz = on_device ? nnz_if_device : (int64_t)rowptr[nrows];
@@ -2411,6 +2414,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
 }
 
 #include "gram.cuh"
+#include "gram_batch.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K0g host side: decide whether G fits, pick its element type, build it (part of staging).
@@ -2447,7 +2451,7 @@ static void build_gram(Matrix *m) {
   }
   if (env_int("SLIMB200_GRAM_F64", 0)) exact32 = false;
   const size_t esz = exact32 ? sizeof(float) : sizeof(double);
-  const size_t ld = ((size_t)ncols + 31) & ~size_t(31);
+  const size_t ld = ((size_t)ncols + 127) & ~size_t(127);  // item-space blocks of up to 128 columns stay inside a row
   const size_t bytes = (size_t)ncols * ld * esz;
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
@@ -2757,6 +2761,52 @@ static int gram_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &
   throw EngineError(kErr, "gram_launch: unsupported cluster size");
 }
 
+constexpr int kBatchT = 8, kBatchV = 2;
+
+template <typename GT, int CS>
+static int batch_launch_t(const SolveArgs &args, const GramArgs &gargs, const BatchArgs &bargs, int count,
+                          cudaStream_t s, bool query_only) {
+  auto kern = cd_gram_batch_kernel<GT, CS, kBatchT, kBatchV>;
+  const size_t dyn = sizeof(BatchSmem<GT, CS, kBatchT, kBatchV>);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)(CS * std::max(count, 1)), 1, 1);
+  cfg.blockDim = dim3(kBatchNT, 1, 1);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = CS > 1 ? 1 : 0;
+  if (query_only) {
+    int n = 0;
+    if (CS == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBatchNT, dyn));
+    else CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    return n;
+  }
+  CK(cudaLaunchKernelEx(&cfg, kern, args, gargs, bargs));
+  return 0;
+}
+
+// cd_gram_batch_kernel: T targets per cluster of `cs` CTAs.  Query: co-resident clusters (CTAs per SM for cs == 1).
+static int batch_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &gargs, const BatchArgs &bargs,
+                        int count, cudaStream_t s, bool query_only) {
+#define SLIM_BATCH_CS(CSV)                                                                         \
+  if (cs == CSV)                                                                                   \
+    return f64 ? batch_launch_t<double, CSV>(args, gargs, bargs, count, s, query_only)             \
+               : batch_launch_t<float, CSV>(args, gargs, bargs, count, s, query_only);
+  SLIM_BATCH_CS(1)
+  SLIM_BATCH_CS(4)
+  SLIM_BATCH_CS(8)
+  SLIM_BATCH_CS(16)
+#undef SLIM_BATCH_CS
+  throw EngineError(kErr, "batch_launch: unsupported cluster size");
+}
+
 static size_t smem_for(int nt, bool ysmem, int32_t nrows) {
   size_t fixed = nt == 32 ? solve_fixed_smem<32>() : nt == 128 ? solve_fixed_smem<128>() : solve_fixed_smem<512>();
   fixed = (fixed + 15) & ~size_t(15);
@@ -2833,7 +2883,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     if (use_gram) cs = 0;
     const bool use_cluster = cs > 0;
     const bool use_window = use_cluster && env_int("SLIMB200_WINDOW", 1) != 0;
-    const size_t col_stride = ((size_t)std::max(ncols, 1) + 3) & ~size_t(3);
+    const size_t col_stride = use_gram ? m->gram_ld : (((size_t)std::max(ncols, 1) + 3) & ~size_t(3));
     const size_t row_stride = ((size_t)std::max(nrows, 1) + 3) & ~size_t(3);
     int nclusters = 0;
     if (use_cluster) {
@@ -2863,25 +2913,45 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
                 plan.nt, plan.ysmem ? "smem" : "global", plan.grid, bps, (int)kernel_vals);
     }
 
-    // Gram-space plan: targets with at least gram_heavy nonzeros go to clusters of gram_cs CTAs, the rest
-    // to single CTAs; the two launches run side by side on two streams.
+    // Gram-space plan, three target classes by column nnz (the target list is sorted by descending nnz):
+    //   nnz >= gram_batch : cd_gram_batch_kernel, T targets per cluster of batch_cs CTAs (item-space blocks)
+    //   nnz >= gram_heavy : cd_gram_kernel on clusters of gram_cs CTAs
+    //   the rest          : cd_gram_kernel, one CTA per target
+    // The launches run side by side on three streams.
     GramArgs gargs{};
+    BatchArgs bargs{};
     int gram_cs = env_int("SLIMB200_GRAM_CS", 8);
     if (gram_cs != 1 && gram_cs != 2 && gram_cs != 4 && gram_cs != 8 && gram_cs != 16) gram_cs = 8;
-    const int gram_heavy = env_int("SLIMB200_GRAM_HEAVY", 1500);
-    int gram_grid_light = 0, gram_clusters = 0;
+    int batch_cs = env_int("SLIMB200_BATCH_CS", 8);
+    if (batch_cs != 1 && batch_cs != 4 && batch_cs != 8 && batch_cs != 16) batch_cs = 8;
+    const int gram_heavy = env_int("SLIMB200_GRAM_HEAVY", 600);
+    const int gram_batch = std::max(gram_heavy, env_int("SLIMB200_GRAM_BATCH", 2500));
+    int gram_grid_light = 0, gram_clusters = 0, batch_clusters = 0;
     if (use_gram) {
+      int32_t nb = 0, nh = 0;  // class sizes of this call
+      for (int32_t q = 0; q < nsel; q++) {
+        const int32_t c = m->h_colcnt[m->h_rank[colof(q)]];
+        if (c >= gram_batch) nb++;
+        else if (gram_cs > 1 && c >= gram_heavy) nh++;
+      }
+      const int32_t nl = nsel - nb - nh;
       gram_grid_light = gram_launch(m->gram_f64, 1, args, gargs, 1, s, true) * m->sm_count;
       gram_clusters = gram_cs > 1 ? gram_launch(m->gram_f64, gram_cs, args, gargs, 1, s, true) : 0;
-      if (gram_grid_light < 1 || (gram_cs > 1 && gram_clusters < 1))
+      batch_clusters = batch_launch(m->gram_f64, batch_cs, args, gargs, bargs, 1, s, true);
+      if (batch_cs == 1) batch_clusters *= m->sm_count;
+      if (gram_grid_light < 1 || (gram_cs > 1 && gram_clusters < 1) || batch_clusters < 1)
         throw EngineError(kErr, "learn: Gram kernel launch configuration not supported on this device");
-      gram_grid_light = std::min(gram_grid_light, std::max(nsel, 1));
-      gram_clusters = std::min(gram_clusters, std::max(nsel, 1));
+      gram_grid_light = std::min(gram_grid_light, std::max(nl, 0));
+      gram_clusters = std::min(gram_clusters, std::max(nh, 0));
+      batch_clusters = std::min(batch_clusters, (nb + kBatchT - 1) / kBatchT);
       if (env_int("SLIMB200_GRAM_CLUSTERS", 0) > 0) gram_clusters = std::min(gram_clusters, env_int("SLIMB200_GRAM_CLUSTERS", 0));
-      plan.grid = gram_grid_light + gram_clusters * gram_cs;
+      if (env_int("SLIMB200_BATCH_CLUSTERS", 0) > 0) batch_clusters = std::min(batch_clusters, env_int("SLIMB200_BATCH_CLUSTERS", 0));
+      plan.grid = std::max(1, batch_clusters * batch_cs + gram_clusters * gram_cs + gram_grid_light);
       if (env_int("SLIMB200_VERBOSE", 0))
-        fprintf(stderr, "[slim-b200] Gram-space kernel (%s G): %d single CTAs + %d clusters of %d CTAs, heavy >= %d nnz\n",
-                m->gram_f64 ? "fp64" : "fp32", gram_grid_light, gram_clusters, gram_cs, gram_heavy);
+        fprintf(stderr, "[slim-b200] Gram-space kernels (%s G): %d targets >= %d nnz on %d clusters of %d CTAs (%d per "
+                        "cluster), %d targets >= %d nnz on %d clusters of %d CTAs, %d targets on %d single CTAs\n",
+                m->gram_f64 ? "fp64" : "fp32", nb, gram_batch, batch_clusters, batch_cs, kBatchT, nh, gram_heavy,
+                gram_clusters, gram_cs, nl, gram_grid_light);
     }
 
     // ---- scratch (cached on the matrix) --------------------------------------------------------
@@ -2902,6 +2972,12 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     const size_t o_gslot = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
     const size_t o_grow = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
     const size_t o_gval = carve(use_gram ? g * col_stride * sizeof(double) : 0);
+    const size_t nbcta = use_gram ? (size_t)batch_clusters * batch_cs : 0;  // the batch CTAs use slots 0 .. nbcta-1
+    const size_t nwords = col_stride / 32;
+    const size_t o_bxt = carve(nbcta * kBatchT * col_stride * sizeof(double));
+    const size_t o_bsv = carve(nbcta * kBatchT * col_stride * sizeof(double));
+    const size_t o_bam = carve(nbcta * kBatchT * nwords * sizeof(uint32_t));
+    const size_t o_ban = carve(nbcta * nwords * sizeof(uint32_t));
     const size_t grp_stride = (size_t)(ncols + 31) / 32 + 1;
     const size_t o_grp = carve(use_cluster ? g * grp_stride * sizeof(GroupMeta) : 0);
     if (off > m->scratch_bytes) {
@@ -2975,6 +3051,12 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       gargs.sl_row = reinterpret_cast<int32_t *>(sb + o_grow);
       gargs.sl_val = reinterpret_cast<double *>(sb + o_gval);
       gargs.expand = m->d_expand;
+      bargs.xt = reinterpret_cast<double *>(sb + o_bxt);
+      bargs.sl_valT = reinterpret_cast<double *>(sb + o_bsv);
+      bargs.amask = reinterpret_cast<uint32_t *>(sb + o_bam);
+      bargs.anym = reinterpret_cast<uint32_t *>(sb + o_ban);
+      bargs.istride = col_stride;
+      bargs.nwords = (int32_t)nwords;
     }
     args.col_stride = col_stride;
     args.row_stride = row_stride;
@@ -3016,7 +3098,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         DevBuf<int32_t> d_ng;
         DevBuf<unsigned long long> d_used;
         d_targets.alloc(nt);
-        d_queue.alloc_zero(2, s);
+        d_queue.alloc_zero(4, s);
         d_used.alloc_zero(1, s);
         d_ocnt.alloc(nt);
         d_ooff.alloc(nt);
@@ -3054,37 +3136,52 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         lp.grid = std::min(plan.grid, nt);
         CK(cudaEventRecord(e0, s));
         if (use_gram) {
-          // `pending` is sorted by descending column nnz: the heavy targets are a prefix
-          int32_t nheavy = 0;
+          // `pending` is sorted by descending column nnz: the classes are consecutive ranges
+          int32_t nb = 0;
+          while (nb < nt && m->h_colcnt[tcols[nb]] >= gram_batch) nb++;
+          int32_t nh = nb;
           if (gram_cs > 1)
-            while (nheavy < nt && m->h_colcnt[tcols[nheavy]] >= gram_heavy) nheavy++;
-          const int32_t nlight = nt - nheavy;
-          cudaStream_t s2 = m->stream2;
-          if (nheavy > 0 && nlight > 0) {
-            CK(cudaEventRecord(e2, s));
-            CK(cudaStreamWaitEvent(s2, e2, 0));
+            while (nh < nt && m->h_colcnt[tcols[nh]] >= gram_heavy) nh++;
+          const int32_t nbatch = nb, nheavy = nh - nb, nlight = nt - nh;
+          cudaStream_t streams[3] = {s, m->stream2, m->stream3};
+          int used = 0;
+          auto next_stream = [&]() {
+            cudaStream_t st = streams[used];
+            if (used > 0) {  // side streams start after everything queued on s so far
+              CK(cudaEventRecord(e2, s));
+              CK(cudaStreamWaitEvent(st, e2, 0));
+            }
+            used++;
+            return st;
+          };
+          GramArgs gq = gargs;
+          if (nbatch > 0) {
+            gq.q_begin = 0;
+            gq.q_end = nbatch;
+            gq.queue = d_queue.p;
+            gq.slot_base = 0;
+            const int ncl = std::max(1, std::min(batch_clusters, (nbatch + kBatchT - 1) / kBatchT));
+            batch_launch(m->gram_f64, batch_cs, args, gq, bargs, ncl, next_stream(), false);
           }
           if (nheavy > 0) {
-            GramArgs gh = gargs;
-            gh.q_begin = 0;
-            gh.q_end = nheavy;
-            gh.queue = d_queue.p;
-            gh.slot_base = 0;
-            gram_launch(m->gram_f64, gram_cs, args, gh, std::min(gram_clusters, nheavy), s, false);
+            gq.q_begin = nbatch;
+            gq.q_end = nbatch + nheavy;
+            gq.queue = d_queue.p + 1;
+            gq.slot_base = batch_clusters * batch_cs;
+            gram_launch(m->gram_f64, gram_cs, args, gq, std::max(1, std::min(gram_clusters, nheavy)), next_stream(), false);
           }
           if (nlight > 0) {
-            GramArgs gl = gargs;
-            gl.q_begin = nheavy;
-            gl.q_end = nt;
-            gl.queue = d_queue.p + 1;
-            gl.slot_base = gram_clusters * gram_cs;
-            gram_launch(m->gram_f64, 1, args, gl, std::min(gram_grid_light, nlight), nheavy > 0 ? s2 : s, false);
-            if (nheavy > 0) {
-              CK(cudaEventRecord(e2, s2));
-              CK(cudaStreamWaitEvent(s, e2, 0));
-              res->tm.launches++;  // two solve launches in this round (the common accounting adds one)
-              res->tm.solve_launches++;
-            }
+            gq.q_begin = nbatch + nheavy;
+            gq.q_end = nt;
+            gq.queue = d_queue.p + 2;
+            gq.slot_base = batch_clusters * batch_cs + gram_clusters * gram_cs;
+            gram_launch(m->gram_f64, 1, args, gq, std::max(1, std::min(gram_grid_light, nlight)), next_stream(), false);
+          }
+          for (int k = 1; k < used; k++) {  // join the side streams
+            CK(cudaEventRecord(e2, streams[k]));
+            CK(cudaStreamWaitEvent(s, e2, 0));
+            res->tm.launches++;  // the common accounting below adds the first launch
+            res->tm.solve_launches++;
           }
           CK(cudaGetLastError());
         } else if (use_cluster) {

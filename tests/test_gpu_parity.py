@@ -295,6 +295,7 @@ def test_gram_matrix_is_exact(lib):
 def test_gram_kernel_variants(lib, ours, oracle, monkeypatch, cs, heavy, ratings, null_vals):
     monkeypatch.setenv("SLIMB200_GRAM_CS", cs)
     monkeypatch.setenv("SLIMB200_GRAM_HEAVY", heavy)
+    monkeypatch.setenv("SLIMB200_GRAM_BATCH", "1000000000")  # not the batched kernel (tested below)
     rp, ri, rv = st.synth_zipf(1000, 260, 24, seed=29, ratings=ratings)
     if null_vals:
         rv = None
@@ -311,6 +312,7 @@ def test_gram_real_valued_ratings(lib, ours, oracle, monkeypatch, cs, heavy, f64
     # non-integer ratings: fp32 sums would not be exact, G is staged in fp64 (also forced on integer data)
     monkeypatch.setenv("SLIMB200_GRAM_CS", cs)
     monkeypatch.setenv("SLIMB200_GRAM_HEAVY", heavy)
+    monkeypatch.setenv("SLIMB200_GRAM_BATCH", "1000000000")  # not the batched kernel (tested below)
     monkeypatch.setenv("SLIMB200_GRAM_F64", f64)
     rp, ri, rv = st.synth_zipf(1200, 240, 20, seed=19, ratings=True)
     if f64 == "0":
@@ -327,6 +329,7 @@ def test_gram_long_columns_and_iteration_cap(lib, ours, oracle, monkeypatch, cs,
     # same case as the user-space kernels: capped head targets must follow the oracle sweep by sweep
     monkeypatch.setenv("SLIMB200_GRAM_CS", cs)
     monkeypatch.setenv("SLIMB200_GRAM_HEAVY", heavy)
+    monkeypatch.setenv("SLIMB200_GRAM_BATCH", "1000000000")  # not the batched kernel (tested below)
     rp, ri, rv = st.synth_zipf(6000, 400, 40, seed=21)
     from slim_b200 import Staged, learn_columns
 
@@ -349,6 +352,7 @@ def test_gram_long_columns_and_iteration_cap(lib, ours, oracle, monkeypatch, cs,
 def test_gram_warm_start(lib, ours, oracle, monkeypatch, cs, heavy):
     monkeypatch.setenv("SLIMB200_GRAM_CS", cs)
     monkeypatch.setenv("SLIMB200_GRAM_HEAVY", heavy)
+    monkeypatch.setenv("SLIMB200_GRAM_BATCH", "1000000000")  # not the batched kernel (tested below)
     rp, ri, rv = st.synth_zipf(900, 200, 20, seed=17, ratings=True)
     h0 = _learn(ours, rp, ri, rv, l1r=3.0, l2r=1.0, niters=30)
     m0 = st.model_views(h0)
@@ -377,6 +381,67 @@ def test_gram_and_user_space_kernels_agree(lib, monkeypatch):
     assert np.array_equal(out["1"][1]["expand_nnz"], out["0"][1]["expand_nnz"])
     _check_close(out["1"][0], out["0"][0], tol=1e-6)
     assert np.allclose(out["1"][1]["objval"], out["0"][1]["objval"], rtol=1e-9)
+
+
+# ---- batched heavy-target kernel (slim_b200/csrc/gram_batch.cuh): 8 targets per cluster, item-space blocks ----
+
+@pytest.mark.parametrize("bcs", ["1", "4", "8", "16"])
+@pytest.mark.parametrize("ratings,null_vals", [(False, False), (True, False), (False, True)])
+def test_gram_batch_kernel_variants(lib, ours, oracle, monkeypatch, bcs, ratings, null_vals):
+    monkeypatch.setenv("SLIMB200_BATCH_CS", bcs)
+    monkeypatch.setenv("SLIMB200_GRAM_BATCH", "0")  # every target goes through the batched kernel
+    monkeypatch.setenv("SLIMB200_GRAM_HEAVY", "0")
+    rp, ri, rv = st.synth_zipf(1000, 260, 24, seed=29, ratings=ratings)
+    if null_vals:
+        rv = None
+    kw = dict(l1r=0.7, l2r=1.5, **CONV)
+    h = _learn(ours, rp, ri, rv, **kw)
+    w = oracle.learn(rp, ri, rv, nthreads=8, **kw, order=st.ORDER_POPULARITY)
+    _check_close(st.model_views(h), w)
+    ours.free(h)
+
+
+@pytest.mark.parametrize("bcs,batch,heavy", [("1", "0", "0"), ("8", "0", "0"), ("16", "0", "0"), ("4", "900", "200"),
+                                             ("8", "2000", "300")])
+def test_gram_batch_long_columns_and_iteration_cap(lib, ours, oracle, monkeypatch, bcs, batch, heavy):
+    # capped head targets follow the oracle sweep by sweep; mixed launches: batched + cluster + single CTA classes
+    monkeypatch.setenv("SLIMB200_BATCH_CS", bcs)
+    monkeypatch.setenv("SLIMB200_GRAM_BATCH", batch)
+    monkeypatch.setenv("SLIMB200_GRAM_HEAVY", heavy)
+    rp, ri, rv = st.synth_zipf(6000, 400, 40, seed=21)
+    from slim_b200 import Staged, learn_columns
+
+    cols = np.arange(0, 400, 7, dtype=np.int32)  # 58 targets: the last batch is short
+    with Staged(rp, ri, rv) as s:
+        r = learn_columns(s, dict(niters=50), cols=cols)
+        got, stats = r.to_host(), r.stats()
+    ref = oracle.learn(rp, ri, rv, niters=50, cols=cols, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
+    assert np.array_equal(stats["nactive"], ref["stats"]["nactive"])
+    assert np.array_equal(stats["active_nnz"], ref["stats"]["active_nnz"])
+    assert np.array_equal(stats["expand_nnz"], ref["stats"]["expand_nnz"])
+    assert np.array_equal(stats["niters"], ref["stats"]["niters"])
+    _check_close(got, ref, tol=1e-6)
+    assert np.allclose(stats["objval"], ref["stats"]["objval"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(stats["rnorm"], ref["stats"]["rnorm"], rtol=1e-9, atol=1e-7)
+
+
+@pytest.mark.parametrize("bcs", ["1", "8"])
+def test_gram_batch_warm_start_and_real_values(lib, ours, oracle, monkeypatch, bcs):
+    monkeypatch.setenv("SLIMB200_BATCH_CS", bcs)
+    monkeypatch.setenv("SLIMB200_GRAM_BATCH", "0")
+    monkeypatch.setenv("SLIMB200_GRAM_HEAVY", "0")
+    rp, ri, rv = st.synth_zipf(900, 200, 20, seed=17, ratings=True)
+    rv = (rv * np.random.default_rng(3).uniform(0.2, 1.0, len(rv))).astype(np.float32)  # fp64 Gram matrix
+    h0 = _learn(ours, rp, ri, rv, l1r=3.0, l2r=1.0, niters=30)
+    m0 = st.model_views(h0)
+    w0 = oracle.learn(rp, ri, rv, l1r=3.0, l2r=1.0, niters=30, nthreads=4, order=st.ORDER_POPULARITY)
+    _check_close(m0, w0, tol=1e-6)
+    h1 = _learn(ours, rp, ri, rv, imodel=h0, l1r=1.0, l2r=1.0, niters=5)
+    w1 = oracle.learn(rp, ri, rv, l1r=1.0, l2r=1.0, niters=5, nthreads=4,
+                      imodel=(m0["ncols"], m0["colptr"], m0["colind"], m0["colval"]), order=st.ORDER_POPULARITY)
+    _check_close(st.model_views(h1), w1, tol=1e-6)
+    for h in (h0, h1):
+        ours.free(h)
 
 
 def test_edge_cases(lib, ours, oracle):
