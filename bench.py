@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SLIM_BENCH_WORKLOAD", "c4"))
-    ap.add_argument("--cols-per-step", type=int, default=int(os.environ.get("SLIM_BENCH_COLS", "592")),
+    ap.add_argument("--cols-per-step", type=int, default=int(os.environ.get("SLIM_BENCH_COLS", "12288")),
                     help="target columns per step PER GPU")
     ap.add_argument("--cpu-cols", type=int, default=int(os.environ.get("SLIM_BENCH_CPU_COLS", "0")),
                     help="columns per reference step (0: four per host thread)")
@@ -345,8 +345,11 @@ def main():
             traffic = json.loads(tf.read_text()).get(args.workload)
         except Exception:
             traffic = None
+    gram_eb, gram_ms = staged.gram_info()
+    kernel_name = ("cd_gram_kernel + cd_gram_batch_kernel (Gram-space CD, concurrent launches)" if gram_eb
+                   else "cd_cluster_kernel (user-space CD)")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "cd_solve_kernel", "peak_source": peak_src,
+                "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms_per_launch": solve_ms / n_launch,
                 "sweep_only_GBps": sweep_b / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0,
                 "mean_sweeps_per_column": float(np.mean(np.concatenate(sweeps_all))) if sweeps_all else 0.0}
@@ -403,7 +406,9 @@ def main():
                     config={"workload": wl_name, "cols_per_step_per_gpu": args.cols_per_step,
                             "parallelism": f"column-sharded x{world}, R replicated",
                             "l2_policy": "inputs (2 GB CSR+CSC) >> 126 MB L2; different columns every step",
-                            "datagen_s": round(gen_s, 2), "stage_ms": round(staged.stage_ms, 2)},
+                            "datagen_s": round(gen_s, 2), "stage_ms": round(staged.stage_ms, 2),
+                            "gram": {"elem_bytes": gram_eb, "build_ms": round(gram_ms, 1),
+                                     "GB": round(gram_eb * staged.ncols * staged.ncols / 1e9, 2)}},
                     roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, clocks=clocks,
                     gpu_launches=int(launches))
         print(json.dumps(line))

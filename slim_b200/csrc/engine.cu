@@ -102,6 +102,16 @@ int device_count() {
   return n;
 }
 
+// Layout of G in HBM: PANEL-major.  A panel is kGramPW consecutive columns of all rows, rows contiguous
+// inside the panel: element (k, i) lives at ((i / PW) * nrows + k) * PW + i % PW.  A block of coordinates
+// then reads one short segment of many rows out of ONE panel (25.6 MB for 100K items) instead of touching
+// every 400 KB row of a 40 GB matrix: few DRAM pages, few TLB entries per block round.
+constexpr int kGramPW = 64;
+__host__ __device__ __forceinline__ size_t gram_off(size_t nr, int k, int i) {
+  return ((size_t)(i / kGramPW) * nr + (size_t)k) * kGramPW + (size_t)(i % kGramPW);
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // staged matrix
 // ------------------------------------------------------------------------------------------------
@@ -134,8 +144,8 @@ struct Matrix {
   double *d_csq = nullptr;
   std::vector<int32_t> h_colcnt;
   // Gram matrix G = R^T R in internal item order (gram.cuh): the Gram-space solver reads rows of it
-  void *d_gram = nullptr;          // float[ncols][gram_ld] (exact integer sums) or double[ncols][gram_ld]
-  size_t gram_ld = 0;
+  void *d_gram = nullptr;          // panel-major (gram_off()), float (exact integer sums) or double elements
+  size_t gram_ld = 0;              // ncols rounded up to whole panels (stride of item-indexed scratch arrays)
   bool gram_f64 = false;
   unsigned long long *d_expand = nullptr;  // per item: sum of len(row_u) over the users of the column
   double gram_ms = 0.0;
@@ -730,8 +740,13 @@ int matrix_gram_to_host(const Matrix *m, void *out) {
     if (!m->d_gram) throw EngineError(kErrInput, "matrix_gram_to_host: no Gram matrix was staged");
     DeviceGuard guard(m->device);
     const size_t esz = m->gram_f64 ? 8 : 4;
-    CK(cudaMemcpy2D(out, (size_t)m->ncols * esz, m->d_gram, m->gram_ld * esz, (size_t)m->ncols * esz,
-                    (size_t)m->ncols, cudaMemcpyDeviceToHost));
+    const size_t n = (size_t)m->ncols;
+    std::vector<unsigned char> tiled((m->gram_ld / kGramPW) * n * kGramPW * esz);
+    CK(cudaMemcpy(tiled.data(), m->d_gram, tiled.size(), cudaMemcpyDeviceToHost));
+    unsigned char *o = static_cast<unsigned char *>(out);
+    for (size_t k = 0; k < n; k++)
+      for (size_t i = 0; i < n; i++)
+        memcpy(o + (k * n + i) * esz, tiled.data() + gram_off(n, (int)k, (int)i) * esz, esz);
     return kOk;
   } catch (const EngineError &e) {
     g_last_error = e.what();
@@ -2452,7 +2467,7 @@ static void build_gram(Matrix *m) {
   if (env_int("SLIMB200_GRAM_F64", 0)) exact32 = false;
   const size_t esz = exact32 ? sizeof(float) : sizeof(double);
   const size_t ld = ((size_t)ncols + 127) & ~size_t(127);  // item-space blocks of up to 128 columns stay inside a row
-  const size_t bytes = (size_t)ncols * ld * esz;
+  const size_t bytes = (ld / kGramPW) * (size_t)ncols * kGramPW * esz;  // whole panels of ncols rows
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t budget = (size_t)env_int("SLIMB200_GRAM_GB", 100) << 30;
@@ -2501,7 +2516,7 @@ static void build_gram(Matrix *m) {
 #define SLIM_GRAM_BUILD(GT, HV)                                                                              \
   gram_build_kernel<GT, HV><<<grid, 256, 0, s>>>(nwork, d_wc.p, d_w0.p, d_w1.p, m->d_colptr, m->d_colind,      \
                                                  m->d_colval, m->d_rowptr, m->d_rowind, m->d_rowval,         \
-                                                 static_cast<GT *>(m->d_gram), ld, m->d_expand)
+                                                 static_cast<GT *>(m->d_gram), (size_t)ncols, m->d_expand)
     if (exact32) {
       if (kv) SLIM_GRAM_BUILD(float, true); else SLIM_GRAM_BUILD(float, false);
     } else {
@@ -2763,11 +2778,12 @@ static int gram_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &
 
 constexpr int kBatchT = 8, kBatchV = 2;
 
-template <typename GT, int CS>
+template <typename GT, int CS, int NTB>
 static int batch_launch_t(const SolveArgs &args, const GramArgs &gargs, const BatchArgs &bargs, int count,
                           cudaStream_t s, bool query_only) {
-  auto kern = cd_gram_batch_kernel<GT, CS, kBatchT, kBatchV>;
-  const size_t dyn = sizeof(BatchSmem<GT, CS, kBatchT, kBatchV>);
+  auto kern = cd_gram_batch_kernel<GT, CS, kBatchT, kBatchV, NTB>;
+  const size_t dyn = sizeof(BatchSmem<GT, CS, kBatchT, kBatchV, NTB>);
+  constexpr int kBatchNT = NTB;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
@@ -2793,12 +2809,15 @@ static int batch_launch_t(const SolveArgs &args, const GramArgs &gargs, const Ba
 }
 
 // cd_gram_batch_kernel: T targets per cluster of `cs` CTAs.  Query: co-resident clusters (CTAs per SM for cs == 1).
-static int batch_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &gargs, const BatchArgs &bargs,
+static int batch_launch(bool f64, int cs, int nt, const SolveArgs &args, const GramArgs &gargs, const BatchArgs &bargs,
                         int count, cudaStream_t s, bool query_only) {
+  // fp64 G: the staging ring of 16 warps would not fit shared memory, 256 threads only
 #define SLIM_BATCH_CS(CSV)                                                                         \
-  if (cs == CSV)                                                                                   \
-    return f64 ? batch_launch_t<double, CSV>(args, gargs, bargs, count, s, query_only)             \
-               : batch_launch_t<float, CSV>(args, gargs, bargs, count, s, query_only);
+  if (cs == CSV) {                                                                                 \
+    if (f64) return batch_launch_t<double, CSV, 256>(args, gargs, bargs, count, s, query_only);    \
+    return nt == 512 ? batch_launch_t<float, CSV, 512>(args, gargs, bargs, count, s, query_only)   \
+                     : batch_launch_t<float, CSV, 256>(args, gargs, bargs, count, s, query_only);  \
+  }
   SLIM_BATCH_CS(1)
   SLIM_BATCH_CS(4)
   SLIM_BATCH_CS(8)
@@ -2922,10 +2941,20 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     BatchArgs bargs{};
     int gram_cs = env_int("SLIMB200_GRAM_CS", 8);
     if (gram_cs != 1 && gram_cs != 2 && gram_cs != 4 && gram_cs != 8 && gram_cs != 16) gram_cs = 8;
-    int batch_cs = env_int("SLIMB200_BATCH_CS", 8);
-    if (batch_cs != 1 && batch_cs != 4 && batch_cs != 8 && batch_cs != 16) batch_cs = 8;
+    // measured on C4 (profiles/): per target the position-space cluster kernel needs fewer SM-seconds than
+    // the batched kernel up to ~30K nonzeros (its active set is sparse in item space); above that the
+    // item-space batches win, and they are the only way to keep the makespan of the few giant targets down
     const int gram_heavy = env_int("SLIMB200_GRAM_HEAVY", 600);
-    const int gram_batch = std::max(gram_heavy, env_int("SLIMB200_GRAM_BATCH", 2500));
+    const int gram_batch = std::max(gram_heavy, env_int("SLIMB200_GRAM_BATCH", 30000));
+    int32_t n_batch_targets = 0;
+    for (int32_t q = 0; use_gram && q < nsel; q++)
+      if (m->h_colcnt[m->h_rank[colof(q)]] >= gram_batch) n_batch_targets++;
+    // few batches: 16-CTA clusters of 512 threads (shortest time per batch); many batches: 8 CTAs of 256
+    // threads, two CTAs per SM (most work per SM-second)
+    const bool few_batches = (n_batch_targets + kBatchT - 1) / kBatchT <= 2 * std::max(1, m->sm_count / 16);
+    int batch_cs = env_int("SLIMB200_BATCH_CS", few_batches ? 16 : 8);
+    if (batch_cs != 1 && batch_cs != 4 && batch_cs != 8 && batch_cs != 16) batch_cs = 8;
+    const int batch_nt = env_int("SLIMB200_BATCH_NT", few_batches && !m->gram_f64 ? 512 : 256) == 512 ? 512 : 256;
     int gram_grid_light = 0, gram_clusters = 0, batch_clusters = 0;
     if (use_gram) {
       int32_t nb = 0, nh = 0;  // class sizes of this call
@@ -2937,7 +2966,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       const int32_t nl = nsel - nb - nh;
       gram_grid_light = gram_launch(m->gram_f64, 1, args, gargs, 1, s, true) * m->sm_count;
       gram_clusters = gram_cs > 1 ? gram_launch(m->gram_f64, gram_cs, args, gargs, 1, s, true) : 0;
-      batch_clusters = batch_launch(m->gram_f64, batch_cs, args, gargs, bargs, 1, s, true);
+      batch_clusters = batch_launch(m->gram_f64, batch_cs, batch_nt, args, gargs, bargs, 1, s, true);
       if (batch_cs == 1) batch_clusters *= m->sm_count;
       if (gram_grid_light < 1 || (gram_cs > 1 && gram_clusters < 1) || batch_clusters < 1)
         throw EngineError(kErr, "learn: Gram kernel launch configuration not supported on this device");
@@ -3044,7 +3073,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     args.act_idx = reinterpret_cast<int32_t *>(sb + o_idx);
     if (use_gram) {
       gargs.G = m->d_gram;
-      gargs.ld = m->gram_ld;
+      gargs.nr = (size_t)ncols;
       gargs.act = reinterpret_cast<int32_t *>(sb + o_idx);
       gargs.x = reinterpret_cast<double *>(sb + o_x);
       gargs.slotp = reinterpret_cast<int32_t *>(sb + o_gslot);
@@ -3057,6 +3086,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       bargs.anym = reinterpret_cast<uint32_t *>(sb + o_ban);
       bargs.istride = col_stride;
       bargs.nwords = (int32_t)nwords;
+      bargs.profile = env_int("SLIMB200_PROFILE", 0);
     }
     args.col_stride = col_stride;
     args.row_stride = row_stride;
@@ -3161,7 +3191,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
             gq.queue = d_queue.p;
             gq.slot_base = 0;
             const int ncl = std::max(1, std::min(batch_clusters, (nbatch + kBatchT - 1) / kBatchT));
-            batch_launch(m->gram_f64, batch_cs, args, gq, bargs, ncl, next_stream(), false);
+            batch_launch(m->gram_f64, batch_cs, batch_nt, args, gq, bargs, ncl, next_stream(), false);
           }
           if (nheavy > 0) {
             gq.q_begin = nbatch;

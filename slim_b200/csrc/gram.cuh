@@ -28,9 +28,11 @@ constexpr int kGramNT = 256;
 constexpr int kGramNW = kGramNT / 32;
 constexpr int kGramUnroll = 16;  // independent gathered loads in flight per lane
 
+// (layout of G: panel-major, see kGramPW / gram_off() in engine.cu)
+
 struct GramArgs {
-  const void *G;  // GT[ncols][ld]
-  size_t ld;
+  const void *G;  // panel-major Gram matrix, see gram_off()
+  size_t nr;      // rows of G (= ncols)
   int32_t q_begin, q_end;  // positions in SolveArgs::targets served by this launch
   int32_t *queue;          // work counter of this launch (starts at 0)
   int32_t slot_base;       // first scratch slot of this launch (slot = slot_base + blockIdx.x)
@@ -59,14 +61,13 @@ __global__ void __launch_bounds__(256) gram_build_kernel(int32_t nwork, const in
                                                          const float *__restrict__ colval,
                                                          const int64_t *__restrict__ rowptr,
                                                          const int32_t *__restrict__ rowind,
-                                                         const float *__restrict__ rowval, GT *G, size_t ld,
+                                                         const float *__restrict__ rowval, GT *G, size_t nr,
                                                          unsigned long long *expand) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int k = wk_col[w];
     const int e0 = wk_e0[w], e1 = wk_e1[w];
     const int64_t c0 = colptr[k];
-    GT *Gk = G + (size_t)k * ld;
     unsigned long long ex = 0;
     // two users per warp iteration keep more loads in flight
     for (int e = e0 + warp * 2; e < e1; e += 16) {
@@ -89,8 +90,8 @@ __global__ void __launch_bounds__(256) gram_build_kernel(int32_t nwork, const in
           if (pa) ra = __ldg(rowval + ta);
           if (pb) rb = __ldg(rowval + tb);
         }
-        if (pa) atomicAdd(Gk + ia, (GT)ra * (GT)va);
-        if (pb) atomicAdd(Gk + ib, (GT)rb * (GT)vb);
+        if (pa) atomicAdd(G + gram_off(nr, k, ia), (GT)ra * (GT)va);
+        if (pb) atomicAdd(G + gram_off(nr, k, ib), (GT)rb * (GT)vb);
         ta += 32;
         tb += 32;
       }
@@ -150,7 +151,7 @@ __device__ __forceinline__ double gram_allsum(GramSmem<CS> &sm, double v, uint32
 
 // partial (this warp's share) of  sum_{e < len} val[e] * G[row[e]][col]  for the lane's column `col`
 template <typename GT>
-__device__ __forceinline__ double gram_gather_sum(const GT *__restrict__ Gcol, size_t ld,
+__device__ __forceinline__ double gram_gather_sum(const GT *__restrict__ Gcol,
                                                   const int32_t *sl_row, const double *sl_val, int len,
                                                   int first_chunk, int chunk_stride) {
   const int lane = threadIdx.x & 31;
@@ -169,7 +170,7 @@ __device__ __forceinline__ double gram_gather_sum(const GT *__restrict__ Gcol, s
 #pragma unroll
       for (int u = 0; u < kGramUnroll; u++) {
         const int r = __shfl_sync(0xffffffffu, row_l, (i0 + u) & 31);
-        g[u] = __ldg(Gcol + (size_t)r * ld);
+        g[u] = __ldg(Gcol + (size_t)r * kGramPW);
       }
 #pragma unroll
       for (int u = 0; u < kGramUnroll; u++) {
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
   int par = 0;
 
   const GT *__restrict__ G = static_cast<const GT *>(ga.G);
-  const size_t ld = ga.ld;
+  const size_t nr = ga.nr;
   const size_t slot = (size_t)(ga.slot_base + blockIdx.x) * a.col_stride;
   int32_t *act = ga.act + slot;
   double *x = ga.x + slot;
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
     if (q >= ga.q_end) break;
     const int j = a.targets[q];
     const int cntj = a.colcnt[j];
-    const GT *__restrict__ Gj = G + (size_t)j * ld;
+    auto gj_at = [&](int i) { return __ldg(G + gram_off(nr, j, i)); };  // aTy_i = G[j][i]
     const bool timer = rank == 0 && tid == 0;
     unsigned long long t_start = 0, t_act = 0, t_sweep = 0;
     if (timer) t_start = globaltimer_ns();
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
     for (int base = 0; base < a.ncols; base += NT) {
       const int i = base + tid;
       double v = 0.0;
-      if (i < a.ncols) v = (double)__ldg(Gj + i);
+      if (i < a.ncols) v = (double)gj_at(i);
       const bool flag = (i < a.ncols) && (i != j) && (v > a.l1r);
       int tot;
       const int pos = na + team_excl_scan<NT>(flag, sm.sc, tot);
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
           const int p0 = b * 32, pm = p0 + lane;
           const bool valid = pm < na;
           const int ab = act[valid ? pm : p0];
-          const GT *__restrict__ Gab = G + ab;
+          const GT *__restrict__ Gab = G + gram_off(nr, 0, ab);  // column ab: row k at + k * PW
           // operands of the chain, requested early (warp 0 only uses them)
           double xv = 0.0, sq = 0.0, den = 1.0, aty = 0.0;
           int myslot = -1;
@@ -322,18 +323,18 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
             const double cn = (double)__ldg(a.cnorms + ab);
             den = cn * cn + a.l2r;
             sq = __ldg(a.csq + ab);
-            aty = (double)(float)(double)__ldg(Gj + ab);  // gk_fkv_t.key is a float (estimate.c:437)
+            aty = (double)(float)(double)gj_at(ab);  // gk_fkv_t.key is a float (estimate.c:437)
           }
           // in-block Gram rows: warp w stages rows 4w .. 4w+3
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             const int r = warp * 4 + u;
-            if (p0 + r < na) s_gbb[r][lane] = __ldg(Gab + (size_t)act[p0 + r] * ld);
+            if (p0 + r < na) s_gbb[r][lane] = __ldg(Gab + (size_t)act[p0 + r] * kGramPW);
           }
           // <a_m, yhat> for the 32 coordinates of the block: this warp's share of the sum over S
           const int len = sm.len;
           sm.part[warp][lane] =
-              gram_gather_sum<GT>(Gab, ld, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW);
+              gram_gather_sum<GT>(Gab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW);
           __syncthreads();
           if (warp == 0) {
             double ipf = 0.0;
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
         const int e = cb * 32 + lane;
         const int col = sl_row[e < len ? e : 0];
         const double vk = e < len ? sl_val[e] : 0.0;
-        const double s = gram_gather_sum<GT>(G + col, ld, sl_row, sl_val, len, warp, NW);
+        const double s = gram_gather_sum<GT>(G + gram_off(nr, 0, col), sl_row, sl_val, len, warp, NW);
         hh = fma(vk, s, hh);
       }
     }
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
       for (int p = tid; p < na; p += NT) {
         const double xv = x[p];
         const double in = fabs(xv) > kEps ? xv : 0.0;
-        yd = fma(in, (double)__ldg(Gj + act[p]), yd);
+        yd = fma(in, (double)gj_at(act[p]), yd);
         reg += 0.5 * a.l2r * xv * xv + a.l1r * fabs(xv);
         nnz_local += in != 0.0 ? 1 : 0;
       }

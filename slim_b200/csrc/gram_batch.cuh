@@ -18,8 +18,6 @@
 // stay bit-identical).
 #pragma once
 
-constexpr int kBatchNT = 256;
-constexpr int kBatchNW = kBatchNT / 32;
 constexpr int kBatchGroup = 8;   // entries per cp.async commit group
 constexpr int kBatchStages = 3;  // groups in a warp's ring (two in flight while one is consumed)
 
@@ -28,8 +26,9 @@ struct BatchArgs {
   double *sl_valT;   // per CTA: [istride][T] effective values of the nonzero-list entries
   uint32_t *amask;   // per CTA: [T][nwords] active-coordinate bits, word w = items 32w .. 32w+31
   uint32_t *anym;    // per CTA: [nwords] OR of amask over the targets of the batch
-  size_t istride;    // >= ncols, multiple of 128 (= GramArgs::ld)
+  size_t istride;    // >= ncols, multiple of 128 (whole panels of G)
   int32_t nwords;    // istride / 32
+  int32_t profile;   // SLIMB200_PROFILE=1: thread 0 of rank 0 prints the cycle split of every batch
 };
 
 template <typename GT, int V>
@@ -80,8 +79,9 @@ struct GVecLoad<double, 4> {
   }
 };
 
-template <typename GT, int CS, int T, int V>
+template <typename GT, int CS, int T, int V, int NTB>
 struct __align__(16) BatchSmem {
+  static constexpr int kBatchNW = NTB / 32;
   static constexpr int TV = T * V;
   static constexpr int OWN = CS > 1 ? TV / CS : 1;  // (target, v) pairs this CTA reduces
   struct Ring {  // per-warp cp.async staging: row segments + entry values
@@ -108,13 +108,13 @@ struct __align__(16) BatchSmem {
 
 // add tagged peer store / wait from engine.cu: st_peer_tagged(), ld_tagged_wait()
 
-template <typename GT, int CS, int T, int V>
-__global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveArgs a, const GramArgs ga,
-                                                                    const BatchArgs ba) {
-  constexpr int NT = kBatchNT, NW = kBatchNW, TV = T * V, BW = 32 * V;  // BW = items per block
+template <typename GT, int CS, int T, int V, int NTB>
+__global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(const SolveArgs a, const GramArgs ga,
+                                                                               const BatchArgs ba) {
+  constexpr int NT = NTB, NW = NTB / 32, TV = T * V, BW = 32 * V;  // BW = items per block
   static_assert(T <= NW, "one chain warp per target");
   static_assert(CS == 1 || (TV % CS == 0 && TV / CS <= NW && CS <= TV), "exchange layout");
-  using Smem = BatchSmem<GT, CS, T, V>;
+  using Smem = BatchSmem<GT, CS, T, V, NTB>;
   extern __shared__ __align__(16) unsigned char batch_smem_raw[];
   Smem &sm = *reinterpret_cast<Smem *>(batch_smem_raw);
 
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
   int par = 0;
 
   const GT *__restrict__ G = static_cast<const GT *>(ga.G);
-  const size_t ld = ga.ld;
+  const size_t nr = ga.nr;
+  static_assert(32 * V == kGramPW, "a block of coordinates is one panel of G");
   const size_t istride = ba.istride;
   const int nwords = ba.nwords;
   const int nblk = (a.ncols + BW - 1) / BW;
@@ -204,10 +205,9 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
         for (int w = tid; w < nwords; w += NT) amask[(size_t)t * nwords + w] = 0u;
         continue;
       }
-      const GT *__restrict__ Gj = G + (size_t)j * ld;
       for (int base = 0; base < (int)istride; base += NT) {
         const int i = base + tid;  // istride is a multiple of 128: all warps stay in range
-        const bool f = i < a.ncols && i != j && (double)__ldg(Gj + i) > a.l1r;
+        const bool f = i < a.ncols && i != j && (double)__ldg(G + gram_off(nr, j, i)) > a.l1r;
         const uint32_t m = __ballot_sync(0xffffffffu, f);
         if (lane == 0 && i < (int)istride) amask[(size_t)t * nwords + (i >> 5)] = m;
         if (f) {
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
           const int r = a.wcolind[k];
           if (r >= 0 && r < a.ncols) {
             const int i = a.rank[r];
-            if (i != j && (double)__ldg(Gj + i) > a.l1r) xt[(size_t)t * istride + i] = (double)a.wcolval[k];
+            if (i != j && (double)__ldg(G + gram_off(nr, j, i)) > a.l1r) xt[(size_t)t * istride + i] = (double)a.wcolval[k];
           }
         }
       }
@@ -269,6 +269,14 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
 #pragma unroll
     for (int t = 0; t < T; t++) hh[t] = 0.0;
     int nvisited = 0;
+    long long pc[6] = {0, 0, 0, 0, 0, 0};  // cycles: gather, wait, exchange, chain, append/publish, rounds
+    long long pt = 0;
+#define SLIM_PT(k)                          \
+  if (ba.profile && tid == 0) {             \
+    const long long now_ = clock64();       \
+    pc[k] += now_ - pt;                     \
+    pt = now_;                              \
+  }
 
     auto gather = [&](int b, double (&acc)[T][V]) {
       // this warp's share of  sum_{e < len} val[e][t] * G[row[e]][block b]  for the lane's V items.
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
       constexpr int GS = kBatchGroup, NG = kBatchStages, GPC = 32 / GS;  // GPC groups per 32-entry chunk
       constexpr int LB = V * (int)sizeof(GT);                           // bytes per lane and entry
       static_assert(LB == 8 || LB == 16, "cp.async element size");
-      const GT *__restrict__ Gblk = G + (size_t)b * BW + (size_t)lane * V;
+      const GT *__restrict__ Gblk = G + gram_off(nr, 0, b * BW) + (size_t)lane * V;  // panel b, row r at + r * PW
       const int len = sm.len;
       const int first = (int)rank * NW + warp, stride = CS * NW;
 #pragma unroll
@@ -297,6 +305,12 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
         const int e = first * 32 + lane;
         row_nxt = e < len ? sl_row[e] : 0;
       }
+      // loop-invariant pieces of the addresses, kept in registers (the compiler otherwise rebuilds them per entry)
+      const char *const g_src0 = reinterpret_cast<const char *>(Gblk);
+      const char *const v_src0 = reinterpret_cast<const char *>(slv + lane);
+      constexpr uint32_t kRowBytes = (uint32_t)(kGramPW * sizeof(GT));  // one row of the panel
+      constexpr uint32_t kSlotG = GS * 32 * LB, kSlotV = GS * T * 8;     // ring bytes per group
+      const bool vlane = lane < T;
       auto issue = [&](int g) {
         if (g < ngr) {
           const int k = g / GPC, i0 = (g % GPC) * GS;
@@ -307,46 +321,53 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
             row_nxt = e < len ? sl_row[e] : 0;
           }
           const int slot = g % NG;
+          const uint32_t gd = g_base + (uint32_t)slot * kSlotG;
+          const uint32_t vd = v_base + (uint32_t)slot * kSlotV;
+          const char *vs = v_src0 + (size_t)(c * 32 + i0) * (T * 8);
 #pragma unroll
           for (int u = 0; u < GS; u++) {
-            const int r = __shfl_sync(0xffffffffu, row_cur, i0 + u);
-            const GT *src = Gblk + (size_t)r * ld;
-            const uint32_t dst = g_base + (uint32_t)((slot * GS + u) * 32 * LB);
-            if (LB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-            else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            if (lane < T) {
-              const double *vs = slv + (size_t)(c * 32 + i0 + u) * T + lane;
-              const uint32_t vd = v_base + (uint32_t)((slot * GS + u) * T * 8);
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(vd), "l"(vs) : "memory");
-            }
+            const uint32_t r = (uint32_t)__shfl_sync(0xffffffffu, row_cur, i0 + u);
+            const char *src = g_src0 + (size_t)r * kRowBytes;
+            if (LB == 8)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(gd + (uint32_t)(u * 32 * LB)), "l"(src) : "memory");
+            else
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gd + (uint32_t)(u * 32 * LB)), "l"(src) : "memory");
+            if (vlane)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(vd + (uint32_t)(u * T * 8)), "l"(vs + u * T * 8) : "memory");
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
+      auto consume_entry = [&](int se) {
+        GT gv[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) gv[v] = ring.g[se][lane][v];
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+          const double val = ring.v[se][0][t];
+#pragma unroll
+          for (int v = 0; v < V; v++) acc[t][v] = fma(val, (double)gv[v], acc[t][v]);
+        }
+      };
 #pragma unroll
       for (int p = 0; p < NG - 1; p++) issue(p);
+      int e0 = first * 32;  // first entry of group g
       for (int g = 0; g < ngr; g++) {
         issue(g + NG - 1);
         asm volatile("cp.async.wait_group %0;" ::"n"(NG - 1) : "memory");
         __syncwarp();
-        const int k = g / GPC, i0 = (g % GPC) * GS;
-        const int e0 = (first + k * stride) * 32 + i0;
         const int slot = g % NG;
+        if (e0 + GS <= len) {  // whole group valid (warp-uniform): no per-entry tests
 #pragma unroll
-        for (int u = 0; u < GS; u++) {
-          if (e0 + u < len) {  // warp-uniform
-            GT gv[V];
+          for (int u = 0; u < GS; u++) consume_entry(slot * GS + u);
+        } else {
 #pragma unroll
-            for (int v = 0; v < V; v++) gv[v] = ring.g[slot * GS + u][lane][v];
-#pragma unroll
-            for (int t = 0; t < T; t++) {
-              const double val = ring.v[slot * GS + u][0][t];
-#pragma unroll
-              for (int v = 0; v < V; v++) acc[t][v] = fma(val, (double)gv[v], acc[t][v]);
-            }
-          }
+          for (int u = 0; u < GS; u++)
+            if (e0 + u < len) consume_entry(slot * GS + u);
         }
         __syncwarp();
+        e0 += GS;
+        if ((g + 1) % GPC == 0) e0 += (stride - 1) * 32;  // next chunk of this warp
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
@@ -383,9 +404,8 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
           act[v] = false;
         }
         if (mine_live) {
-          const GT *__restrict__ Gj = G + (size_t)myj * ld;
           GT gj[V];
-          GVecLoad<GT, V>::ld(Gj + item0, gj);
+          GVecLoad<GT, V>::ld(G + gram_off(nr, myj, item0), gj);
 #pragma unroll
           for (int v = 0; v < V; v++) {
             const int i = item0 + v;
@@ -404,17 +424,20 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
           GT row[V];
 #pragma unroll
           for (int v = 0; v < V; v++) row[v] = (GT)0;
-          if (b * BW + r < a.ncols) GVecLoad<GT, V>::ld(G + (size_t)(b * BW + r) * ld + item0, row);
+          if (b * BW + r < a.ncols) GVecLoad<GT, V>::ld(G + gram_off(nr, b * BW + r, item0), row);
 #pragma unroll
           for (int v = 0; v < V; v++) sm.gbb[r][lane * V + v] = row[v];
         }
         double acc[T][V];
+        if (ba.profile && tid == 0) pt = clock64();
         gather(b, acc);
+        SLIM_PT(0)
 #pragma unroll
         for (int t = 0; t < T; t++)
 #pragma unroll
           for (int v = 0; v < V; v++) sm.w[warp].part[t][v][lane] = acc[t][v];
         __syncthreads();
+        SLIM_PT(1)
 
         // reduce over the warps (and the CTAs of the cluster): warp t ends with target t's V sums
         double ipf[V];
@@ -452,6 +475,7 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
           }
         }
 
+        SLIM_PT(2)
         // ---- chains: warp t, exact sequential CD over the block in ascending item order ---------
         double xn[V];
         uint32_t appm[V];
@@ -512,6 +536,7 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
 #pragma unroll
           for (int v = 0; v < V; v++) sm.newmask[warp][v] = appm[v];
         }
+        SLIM_PT(3)
         __syncthreads();
         // ---- warp 0 appends the new entries (union over targets) in ascending item order ----------
         if (warp == 0) {
@@ -558,6 +583,8 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
           }
         }
         __syncthreads();
+        SLIM_PT(4)
+        pc[5]++;
       }
       // ---- end of sweep: stop rule per target (cd.c:135-138)
       if (warp < T) {
@@ -577,6 +604,11 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
     }
     if (tid < T && sm.target[tid] >= 0 && sm.maxit[tid] <= 0) sm.niters[tid] = 1;
     if (timer) t_sweep = globaltimer_ns();
+    if (ba.profile && rank == 0 && tid == 0)
+      printf("[batch q0=%d teff=%d len=%d] rounds %lld  cycles/round: gather %lld  wait %lld  exchange %lld  chain %lld  "
+             "append+publish %lld\n", q0, teff, sm.len, pc[5], pc[0] / max(pc[5], 1LL), pc[1] / max(pc[5], 1LL),
+             pc[2] / max(pc[5], 1LL), pc[3] / max(pc[5], 1LL), pc[4] / max(pc[5], 1LL));
+#undef SLIM_PT
 
     // ---- residual / objective (estimate.c:477-489): hh_t = sum_i x_t[i] <a_i, yhat_t> ------------
     for (int b = 0; b < nblk; b++) {
@@ -620,7 +652,6 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
       for (int t = 0; t < teff; t++) {
         const int j = sm.target[t];
         const int q = q0 + t;
-        const GT *__restrict__ Gj = G + (size_t)j * ld;
         const double *x = xt + (size_t)t * istride;
         double yd = 0.0, reg = 0.0;
         int nnz_local = 0;
@@ -628,7 +659,7 @@ __global__ void __launch_bounds__(kBatchNT, 2) cd_gram_batch_kernel(const SolveA
           const double xv = x[i];
           if (xv != 0.0) {
             const double in = fabs(xv) > kEps ? xv : 0.0;
-            yd = fma(in, (double)__ldg(Gj + i), yd);
+            yd = fma(in, (double)__ldg(G + gram_off(nr, j, i)), yd);
             reg += 0.5 * a.l2r * xv * xv + a.l1r * fabs(xv);
             nnz_local += in != 0.0 ? 1 : 0;
           }
