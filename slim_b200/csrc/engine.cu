@@ -152,6 +152,7 @@ struct Matrix {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // extra streams: the Gram launches of the target classes run side by side
   cudaStream_t stream3 = nullptr;
+  cudaStream_t stream4 = nullptr;
   int sm_count = 0;
   int smem_optin = 0;
   double stage_ms = 0.0;
@@ -182,6 +183,7 @@ void free_matrix(Matrix *m) {
   cudaFree(m->d_expand);
   if (m->stream2) cudaStreamDestroy(m->stream2);
   if (m->stream3) cudaStreamDestroy(m->stream3);
+  if (m->stream4) cudaStreamDestroy(m->stream4);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -484,6 +486,7 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
     CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m->stream3, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&m->stream4, cudaStreamNonBlocking));
     cudaStream_t s = m->stream;
     m->nrows = nrows;
     m->nnz = on_device ? nnz_if_device : (int64_t)rowptr[nrows];
@@ -2932,55 +2935,73 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
                 plan.nt, plan.ysmem ? "smem" : "global", plan.grid, bps, (int)kernel_vals);
     }
 
-    // Gram-space plan, three target classes by column nnz (the target list is sorted by descending nnz):
-    //   nnz >= gram_batch : cd_gram_batch_kernel, T targets per cluster of batch_cs CTAs (item-space blocks)
-    //   nnz >= gram_heavy : cd_gram_kernel on clusters of gram_cs CTAs
+    // Gram-space plan: target classes by column nnz (the target list is sorted by descending nnz), one launch
+    // per class, all launches side by side on their own streams:
+    //   nnz >= gram_top   : cd_gram_batch_kernel, 8 targets per cluster; when there are only a few such batches,
+    //                       16 CTAs x 512 threads per batch (shortest time per batch -- they set the makespan)
+    //   nnz >= gram_batch : cd_gram_batch_kernel, clusters of 8 CTAs x 256 threads, two CTAs per SM (most work
+    //                       per SM-second when there are many batches; empty by default, see below)
+    //   nnz >= gram_heavy : cd_gram_kernel on clusters of gram_cs CTAs (position-space blocks)
     //   the rest          : cd_gram_kernel, one CTA per target
-    // The launches run side by side on three streams.
     GramArgs gargs{};
     BatchArgs bargs{};
-    int gram_cs = env_int("SLIMB200_GRAM_CS", 8);
-    if (gram_cs != 1 && gram_cs != 2 && gram_cs != 4 && gram_cs != 8 && gram_cs != 16) gram_cs = 8;
-    // measured on C4 (profiles/): per target the position-space cluster kernel needs fewer SM-seconds than
-    // the batched kernel up to ~30K nonzeros (its active set is sparse in item space); above that the
-    // item-space batches win, and they are the only way to keep the makespan of the few giant targets down
-    const int gram_heavy = env_int("SLIMB200_GRAM_HEAVY", 600);
-    const int gram_batch = std::max(gram_heavy, env_int("SLIMB200_GRAM_BATCH", 30000));
-    int32_t n_batch_targets = 0;
-    for (int32_t q = 0; use_gram && q < nsel; q++)
-      if (m->h_colcnt[m->h_rank[colof(q)]] >= gram_batch) n_batch_targets++;
-    // few batches: 16-CTA clusters of 512 threads (shortest time per batch); many batches: 8 CTAs of 256
-    // threads, two CTAs per SM (most work per SM-second)
-    const bool few_batches = (n_batch_targets + kBatchT - 1) / kBatchT <= 2 * std::max(1, m->sm_count / 16);
-    int batch_cs = env_int("SLIMB200_BATCH_CS", few_batches ? 16 : 8);
-    if (batch_cs != 1 && batch_cs != 4 && batch_cs != 8 && batch_cs != 16) batch_cs = 8;
-    const int batch_nt = env_int("SLIMB200_BATCH_NT", few_batches && !m->gram_f64 ? 512 : 256) == 512 ? 512 : 256;
-    int gram_grid_light = 0, gram_clusters = 0, batch_clusters = 0;
+    struct GramClass {
+      bool batch;
+      int cs, nt;      // CTAs per cluster, threads per CTA
+      int min_nnz;     // class = targets with min_nnz <= nnz < min_nnz of the previous class
+      int ntargets;    // of this call
+      int units;       // clusters (CTAs for cs == 1) to launch at most
+      int slot_base;   // first scratch slot (CTA granularity)
+    };
+    std::vector<GramClass> classes;
     if (use_gram) {
-      int32_t nb = 0, nh = 0;  // class sizes of this call
+      int gram_cs = env_int("SLIMB200_GRAM_CS", 8);
+      if (gram_cs != 1 && gram_cs != 2 && gram_cs != 4 && gram_cs != 8 && gram_cs != 16) gram_cs = 8;
+      const int gram_heavy = env_int("SLIMB200_GRAM_HEAVY", 600);
+      // measured on C4 (profiles/r01_gram_class_routing.txt): below ~30K nonzeros a batch of 8 targets costs more
+      // SM-seconds than eight one-target clusters (the union nonzero list is much longer than each target's own and
+      // the item-space blocks cover inactive coordinates), so by default the two batch classes coincide
+      const int gram_batch = std::max(gram_heavy, env_int("SLIMB200_GRAM_BATCH", 30000));
+      const int gram_top = std::max(gram_batch, env_int("SLIMB200_GRAM_TOP", 30000));
+      int32_t ntop = 0;
+      for (int32_t q = 0; q < nsel; q++)
+        if (m->h_colcnt[m->h_rank[colof(q)]] >= gram_top) ntop++;
+      const bool few_top = (ntop + kBatchT - 1) / kBatchT <= 2 * std::max(1, m->sm_count / 16);
+      auto batch_cs_of = [&](int dflt) {
+        const int v = env_int("SLIMB200_BATCH_CS", dflt);
+        return (v == 1 || v == 4 || v == 8 || v == 16) ? v : dflt;
+      };
+      auto batch_nt_of = [&](int dflt) {
+        return (!m->gram_f64 && env_int("SLIMB200_BATCH_NT", dflt) == 512) ? 512 : 256;
+      };
+      classes.push_back({true, batch_cs_of(few_top ? 16 : 8), batch_nt_of(few_top ? 512 : 256), gram_top, 0, 0, 0});
+      classes.push_back({true, batch_cs_of(8), batch_nt_of(256), gram_batch, 0, 0, 0});
+      if (gram_cs > 1) classes.push_back({false, gram_cs, kGramNT, gram_heavy, 0, 0, 0});
+      classes.push_back({false, 1, kGramNT, INT32_MIN, 0, 0, 0});
       for (int32_t q = 0; q < nsel; q++) {
         const int32_t c = m->h_colcnt[m->h_rank[colof(q)]];
-        if (c >= gram_batch) nb++;
-        else if (gram_cs > 1 && c >= gram_heavy) nh++;
+        for (auto &gc : classes)
+          if (c >= gc.min_nnz) {
+            gc.ntargets++;
+            break;
+          }
       }
-      const int32_t nl = nsel - nb - nh;
-      gram_grid_light = gram_launch(m->gram_f64, 1, args, gargs, 1, s, true) * m->sm_count;
-      gram_clusters = gram_cs > 1 ? gram_launch(m->gram_f64, gram_cs, args, gargs, 1, s, true) : 0;
-      batch_clusters = batch_launch(m->gram_f64, batch_cs, batch_nt, args, gargs, bargs, 1, s, true);
-      if (batch_cs == 1) batch_clusters *= m->sm_count;
-      if (gram_grid_light < 1 || (gram_cs > 1 && gram_clusters < 1) || batch_clusters < 1)
-        throw EngineError(kErr, "learn: Gram kernel launch configuration not supported on this device");
-      gram_grid_light = std::min(gram_grid_light, std::max(nl, 0));
-      gram_clusters = std::min(gram_clusters, std::max(nh, 0));
-      batch_clusters = std::min(batch_clusters, (nb + kBatchT - 1) / kBatchT);
-      if (env_int("SLIMB200_GRAM_CLUSTERS", 0) > 0) gram_clusters = std::min(gram_clusters, env_int("SLIMB200_GRAM_CLUSTERS", 0));
-      if (env_int("SLIMB200_BATCH_CLUSTERS", 0) > 0) batch_clusters = std::min(batch_clusters, env_int("SLIMB200_BATCH_CLUSTERS", 0));
-      plan.grid = std::max(1, batch_clusters * batch_cs + gram_clusters * gram_cs + gram_grid_light);
-      if (env_int("SLIMB200_VERBOSE", 0))
-        fprintf(stderr, "[slim-b200] Gram-space kernels (%s G): %d targets >= %d nnz on %d clusters of %d CTAs (%d per "
-                        "cluster), %d targets >= %d nnz on %d clusters of %d CTAs, %d targets on %d single CTAs\n",
-                m->gram_f64 ? "fp64" : "fp32", nb, gram_batch, batch_clusters, batch_cs, kBatchT, nh, gram_heavy,
-                gram_clusters, gram_cs, nl, gram_grid_light);
+      int slots = 0;
+      for (auto &gc : classes) {
+        int hw = gc.batch ? batch_launch(m->gram_f64, gc.cs, gc.nt, args, gargs, bargs, 1, s, true)
+                          : gram_launch(m->gram_f64, gc.cs, args, gargs, 1, s, true);
+        if (gc.cs == 1) hw *= m->sm_count;
+        if (hw < 1) throw EngineError(kErr, "learn: Gram kernel launch configuration not supported on this device");
+        const int need = gc.batch ? (gc.ntargets + kBatchT - 1) / kBatchT : gc.ntargets;
+        gc.units = std::min(hw, need);
+        gc.slot_base = slots;
+        slots += gc.units * gc.cs;
+        if (env_int("SLIMB200_VERBOSE", 0) && gc.ntargets > 0)
+          fprintf(stderr, "[slim-b200] Gram-space (%s G): %d targets with nnz >= %d -> %s, %d x (%d CTAs x %d threads)\n",
+                  m->gram_f64 ? "fp64" : "fp32", gc.ntargets, gc.min_nnz,
+                  gc.batch ? "cd_gram_batch_kernel (8 targets per cluster)" : "cd_gram_kernel", gc.units, gc.cs, gc.nt);
+      }
+      plan.grid = std::max(1, slots);
     }
 
     // ---- scratch (cached on the matrix) --------------------------------------------------------
@@ -3001,7 +3022,9 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     const size_t o_gslot = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
     const size_t o_grow = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
     const size_t o_gval = carve(use_gram ? g * col_stride * sizeof(double) : 0);
-    const size_t nbcta = use_gram ? (size_t)batch_clusters * batch_cs : 0;  // the batch CTAs use slots 0 .. nbcta-1
+    size_t nbcta = 0;  // the batch classes come first: their CTAs use slots 0 .. nbcta-1
+    for (const auto &gc : classes)
+      if (gc.batch) nbcta += (size_t)gc.units * gc.cs;
     const size_t nwords = col_stride / 32;
     const size_t o_bxt = carve(nbcta * kBatchT * col_stride * sizeof(double));
     const size_t o_bsv = carve(nbcta * kBatchT * col_stride * sizeof(double));
@@ -3167,13 +3190,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         CK(cudaEventRecord(e0, s));
         if (use_gram) {
           // `pending` is sorted by descending column nnz: the classes are consecutive ranges
-          int32_t nb = 0;
-          while (nb < nt && m->h_colcnt[tcols[nb]] >= gram_batch) nb++;
-          int32_t nh = nb;
-          if (gram_cs > 1)
-            while (nh < nt && m->h_colcnt[tcols[nh]] >= gram_heavy) nh++;
-          const int32_t nbatch = nb, nheavy = nh - nb, nlight = nt - nh;
-          cudaStream_t streams[3] = {s, m->stream2, m->stream3};
+          cudaStream_t streams[4] = {s, m->stream2, m->stream3, m->stream4};
           int used = 0;
           auto next_stream = [&]() {
             cudaStream_t st = streams[used];
@@ -3184,28 +3201,25 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
             used++;
             return st;
           };
-          GramArgs gq = gargs;
-          if (nbatch > 0) {
-            gq.q_begin = 0;
-            gq.q_end = nbatch;
-            gq.queue = d_queue.p;
-            gq.slot_base = 0;
-            const int ncl = std::max(1, std::min(batch_clusters, (nbatch + kBatchT - 1) / kBatchT));
-            batch_launch(m->gram_f64, batch_cs, batch_nt, args, gq, bargs, ncl, next_stream(), false);
-          }
-          if (nheavy > 0) {
-            gq.q_begin = nbatch;
-            gq.q_end = nbatch + nheavy;
-            gq.queue = d_queue.p + 1;
-            gq.slot_base = batch_clusters * batch_cs;
-            gram_launch(m->gram_f64, gram_cs, args, gq, std::max(1, std::min(gram_clusters, nheavy)), next_stream(), false);
-          }
-          if (nlight > 0) {
-            gq.q_begin = nbatch + nheavy;
-            gq.q_end = nt;
-            gq.queue = d_queue.p + 2;
-            gq.slot_base = batch_clusters * batch_cs + gram_clusters * gram_cs;
-            gram_launch(m->gram_f64, 1, args, gq, std::max(1, std::min(gram_grid_light, nlight)), next_stream(), false);
+          int32_t q_next = 0;
+          int ci = 0;
+          for (const auto &gc : classes) {
+            int32_t q_end = q_next;
+            while (q_end < nt && m->h_colcnt[tcols[q_end]] >= gc.min_nnz) q_end++;
+            const int32_t ncl_targets = q_end - q_next;
+            if (ncl_targets > 0) {
+              GramArgs gq = gargs;
+              gq.q_begin = q_next;
+              gq.q_end = q_end;
+              gq.queue = d_queue.p + ci;
+              gq.slot_base = gc.slot_base;
+              const int need = gc.batch ? (ncl_targets + kBatchT - 1) / kBatchT : ncl_targets;
+              const int units = std::max(1, std::min(gc.units, need));
+              if (gc.batch) batch_launch(m->gram_f64, gc.cs, gc.nt, args, gq, bargs, units, next_stream(), false);
+              else gram_launch(m->gram_f64, gc.cs, args, gq, units, next_stream(), false);
+            }
+            q_next = q_end;
+            ci++;
           }
           for (int k = 1; k < used; k++) {  // join the side streams
             CK(cudaEventRecord(e2, streams[k]));
