@@ -148,6 +148,8 @@ struct Matrix {
   size_t gram_ld = 0;              // ncols rounded up to whole panels (stride of item-indexed scratch arrays)
   bool gram_f64 = false;
   unsigned long long *d_expand = nullptr;  // per item: sum of len(row_u) over the users of the column
+  void *d_gcache = nullptr;                // row cache of the one-target Gram clusters (gram.cuh)
+  size_t gcache_bytes = 0;
   double gram_ms = 0.0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // extra streams: the Gram launches of the target classes run side by side
@@ -180,6 +182,7 @@ void free_matrix(Matrix *m) {
   cudaFree(m->d_inv);
   cudaFree(m->d_scratch);
   cudaFree(m->d_gram);
+  cudaFree(m->d_gcache);
   cudaFree(m->d_expand);
   if (m->stream2) cudaStreamDestroy(m->stream2);
   if (m->stream3) cudaStreamDestroy(m->stream3);
@@ -3022,6 +3025,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     const size_t o_gslot = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
     const size_t o_grow = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
     const size_t o_gval = carve(use_gram ? g * col_stride * sizeof(double) : 0);
+    const size_t o_gcpp = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
+    const size_t o_gcps = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
     size_t nbcta = 0;  // the batch classes come first: their CTAs use slots 0 .. nbcta-1
     for (const auto &gc : classes)
       if (gc.batch) nbcta += (size_t)gc.units * gc.cs;
@@ -3103,6 +3108,44 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       gargs.sl_row = reinterpret_cast<int32_t *>(sb + o_grow);
       gargs.sl_val = reinterpret_cast<double *>(sb + o_gval);
       gargs.expand = m->d_expand;
+      gargs.cposp = reinterpret_cast<int32_t *>(sb + o_gcpp);
+      gargs.sl_cpos = reinterpret_cast<int32_t *>(sb + o_gcps);
+      // row cache for the one-target cluster class: SLIMB200_GRAM_CACHE_MB per cluster (default 0 = off: measured
+      // neutral on C4, profiles/r01_gram_class_routing.txt),
+      // shrunk to what is free (another staged matrix may hold its own G and cache)
+      gargs.cache = nullptr;
+      gargs.cache_elems = 0;
+      int cache_clusters = 0;
+      for (const auto &gc : classes)
+        if (!gc.batch && gc.cs > 1) cache_clusters = gc.units;
+      const size_t want_mb = (size_t)std::max(0, env_int("SLIMB200_GRAM_CACHE_MB", 0));
+      if (cache_clusters > 0 && want_mb > 0) {
+        // never more than a whole target needs: every row of an all-active target
+        const size_t whole = (size_t)ncols * col_stride * (m->gram_f64 ? 8 : 4);
+        size_t need = (size_t)cache_clusters * std::min(want_mb << 20, whole);
+        if (need > m->gcache_bytes) {
+          cudaFree(m->d_gcache);
+          m->d_gcache = nullptr;
+          m->gcache_bytes = 0;
+          size_t free_b = 0, total_b = 0;
+          CK(cudaMemGetInfo(&free_b, &total_b));
+          const size_t reserve = (size_t)8 << 30;
+          const size_t avail = free_b > reserve ? free_b - reserve : 0;
+          need = std::min(need, avail);
+          if (need / cache_clusters >= (size_t)4096 && cudaMalloc(&m->d_gcache, need) == cudaSuccess)
+            m->gcache_bytes = need;
+          else
+            (void)cudaGetLastError();
+        }
+        if (m->d_gcache) {
+          const size_t esz = m->gram_f64 ? 8 : 4;
+          gargs.cache = m->d_gcache;
+          gargs.cache_elems = (std::min(m->gcache_bytes, need) / cache_clusters / esz) & ~size_t(31);
+          if (env_int("SLIMB200_VERBOSE", 0))
+            fprintf(stderr, "[slim-b200] Gram row cache: %d clusters x %.0f MB\n", cache_clusters,
+                    gargs.cache_elems * esz / 1048576.0);
+        }
+      }
       bargs.xt = reinterpret_cast<double *>(sb + o_bxt);
       bargs.sl_valT = reinterpret_cast<double *>(sb + o_bsv);
       bargs.amask = reinterpret_cast<uint32_t *>(sb + o_bam);
@@ -3192,12 +3235,12 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
           // `pending` is sorted by descending column nnz: the classes are consecutive ranges
           cudaStream_t streams[4] = {s, m->stream2, m->stream3, m->stream4};
           int used = 0;
+          // fork point: the side streams wait for the copies / memsets queued on s so far, NOT for the
+          // launches that follow on s (the classes must overlap)
+          CK(cudaEventRecord(e2, s));
           auto next_stream = [&]() {
             cudaStream_t st = streams[used];
-            if (used > 0) {  // side streams start after everything queued on s so far
-              CK(cudaEventRecord(e2, s));
-              CK(cudaStreamWaitEvent(st, e2, 0));
-            }
+            if (used > 0) CK(cudaStreamWaitEvent(st, e2, 0));
             used++;
             return st;
           };

@@ -43,6 +43,13 @@ struct GramArgs {
   int32_t *sl_row;  // nonzero list: item id ...
   double *sl_val;   // ... and effective value (0 for a coordinate that went back to zero)
   const unsigned long long *expand;  // per item: sum of row lengths over the users of the column
+  // Row cache of the one-target cluster launch (CS > 1): the first time a coordinate becomes nonzero, its Gram
+  // row RESTRICTED TO THE ACTIVE SET is gathered once into a contiguous buffer shared by the cluster; every
+  // later block round reads 128 contiguous bytes of it instead of 32 scattered sectors of G.
+  void *cache;          // GT[clusters][cache_elems], nullptr = no cache
+  size_t cache_elems;   // elements per cluster
+  int32_t *cposp;       // per CTA, per active coordinate: its cache row or -1
+  int32_t *sl_cpos;     // per CTA, per list entry: cache row or -1
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -125,6 +132,8 @@ struct __align__(16) GramSmem {
   int len;    // entries in the nonzero list
   int nzero;  // ... of which currently zero
   int done;
+  int ncached;  // cache rows handed out for the current target
+  int napp;     // entries appended in the current block round
 };
 
 __device__ __forceinline__ uint32_t gram_cluster_rank() {
@@ -149,20 +158,24 @@ __device__ __forceinline__ double gram_allsum(GramSmem<CS> &sm, double v, uint32
   return s;
 }
 
-// partial (this warp's share) of  sum_{e < len} val[e] * G[row[e]][col]  for the lane's column `col`
-template <typename GT>
-__device__ __forceinline__ double gram_gather_sum(const GT *__restrict__ Gcol,
-                                                  const int32_t *sl_row, const double *sl_val, int len,
-                                                  int first_chunk, int chunk_stride) {
+// partial (this warp's share) of  sum_{e < len} val[e] * G[row[e]][col]  for the lane's column `col`.
+// CACHED: entries with sl_cpos[e] >= 0 are read from the row cache (crow = cache + block position + lane,
+// rows npad apart) through L2 (the rows were written by another CTA of the cluster).
+template <typename GT, bool CACHED>
+__device__ __forceinline__ double gram_gather_sum(const GT *__restrict__ Gcol, const int32_t *sl_row,
+                                                  const double *sl_val, int len, int first_chunk, int chunk_stride,
+                                                  const int32_t *sl_cpos = nullptr, const GT *crow = nullptr,
+                                                  size_t npad = 0) {
   const int lane = threadIdx.x & 31;
   double acc = 0.0;
   for (int c = first_chunk; c * 32 < len; c += chunk_stride) {
     const int e = c * 32 + lane;
-    int row_l = 0;
+    int row_l = 0, cp_l = -1;
     double val_l = 0.0;
     if (e < len) {
       row_l = sl_row[e];
       val_l = sl_val[e];
+      if (CACHED) cp_l = sl_cpos[e];
     }
     const int cnt = min(32, len - c * 32);
     for (int i0 = 0; i0 < cnt; i0 += kGramUnroll) {
@@ -170,7 +183,14 @@ __device__ __forceinline__ double gram_gather_sum(const GT *__restrict__ Gcol,
 #pragma unroll
       for (int u = 0; u < kGramUnroll; u++) {
         const int r = __shfl_sync(0xffffffffu, row_l, (i0 + u) & 31);
-        g[u] = __ldg(Gcol + (size_t)r * kGramPW);
+        if (CACHED) {
+          const int cp = __shfl_sync(0xffffffffu, cp_l, (i0 + u) & 31);
+          // one load instruction for both sources (L2 only: the cache rows were written by peer CTAs)
+          const GT *src = cp >= 0 ? crow + (size_t)cp * npad : Gcol + (size_t)r * kGramPW;
+          g[u] = __ldcg(src);
+        } else {
+          g[u] = __ldg(Gcol + (size_t)r * kGramPW);
+        }
       }
 #pragma unroll
       for (int u = 0; u < kGramUnroll; u++) {
@@ -201,6 +221,9 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
   int32_t *slotp = ga.slotp + slot;
   int32_t *sl_row = ga.sl_row + slot;
   double *sl_val = ga.sl_val + slot;
+  int32_t *cposp = ga.cposp + slot;
+  int32_t *sl_cpos = ga.sl_cpos + slot;
+  GT *const cache = (CS > 1 && ga.cache) ? static_cast<GT *>(ga.cache) + (size_t)(blockIdx.x / CS) * ga.cache_elems : nullptr;
   float *xw = a.xw ? a.xw + slot : nullptr;
 
   if (CS > 1) {
@@ -256,6 +279,7 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
       if (flag) {
         act[pos] = i;
         x[pos] = warm ? (double)xw[i] : 0.0;
+        cposp[pos] = -1;
         actnnz += a.colcnt[i];
       }
       na += tot;
@@ -282,6 +306,7 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
         if (flag) {
           sl_row[pos] = act[p];
           sl_val[pos] = xv;
+          sl_cpos[pos] = cposp[p];
         }
         len += tot;
       }
@@ -289,9 +314,14 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
       if (tid == 0) {
         sm.len = len;
         sm.nzero = 0;
+        sm.napp = 0;
       }
       __syncthreads();
     };
+    const size_t npad = ((size_t)na + 31) & ~size_t(31);
+    const size_t rows_fit = ga.cache_elems / (npad ? npad : 32);
+    const int rows_cap = cache ? (int)(rows_fit < (size_t)0x7fffffff ? rows_fit : (size_t)0x7fffffff) : 0;
+    if (tid == 0) sm.ncached = 0;
     rebuild_list();
 
     // ---- iteration cap (estimate.c:448-449)
@@ -334,7 +364,9 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
           // <a_m, yhat> for the 32 coordinates of the block: this warp's share of the sum over S
           const int len = sm.len;
           sm.part[warp][lane] =
-              gram_gather_sum<GT>(Gab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW);
+              cache ? gram_gather_sum<GT, true>(Gab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW, sl_cpos,
+                                                cache + p0 + lane, npad)
+                    : gram_gather_sum<GT, false>(Gab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW);
           __syncthreads();
           if (warp == 0) {
             double ipf = 0.0;
@@ -373,18 +405,65 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
             const unsigned zerm = __ballot_sync(0xffffffffu, chg && myslot >= 0 && now == 0.0);
             const unsigned revm = __ballot_sync(0xffffffffu, chg && myslot >= 0 && was == 0.0);
             if (chg && myslot >= 0) sl_val[myslot] = now;
+            const int ncached0 = sm.ncached;
+            const int oldcp = (app && cache) ? cposp[pm] : -1;  // a coordinate that re-enters the list keeps its row
+            const unsigned needm = __ballot_sync(0xffffffffu, app && oldcp < 0);
             if (app) {
               const int pos = len + __popc(appm & ((1u << lane) - 1u));
+              const int want = ncached0 + __popc(needm & ((1u << lane) - 1u));
+              const int cp = oldcp >= 0 ? oldcp : (want < rows_cap ? want : -1);  // a cache row while there is room
               sl_row[pos] = ab;
               sl_val[pos] = now;
+              sl_cpos[pos] = cp;
+              cposp[pm] = cp;
               slotp[pm] = pos;
             }
             if (lane == 0) {
-              sm.len = len + __popc(appm);
+              const int napp = __popc(appm);
+              sm.len = len + napp;
+              sm.napp = napp;
+              sm.ncached = min(rows_cap, ncached0 + __popc(needm));
               sm.nzero += __popc(zerm) - __popc(revm);
             }
           }
           __syncthreads();
+          if (CS > 1 && cache != nullptr) {
+            // fill the cache rows handed out in this round: row k restricted to the active set, contiguous.
+            // The new entries are dealt over the CTAs of the cluster; a cluster barrier (release / acquire)
+            // publishes the rows before anyone's next gather reads them.  napp is identical in all CTAs.
+            const int napp = sm.napp;
+            if (napp > 0) {
+              const int first_e = sm.len - napp;
+              for (int i = 0; i < napp; i++) {
+                const int e = first_e + i;
+                const int cp = sl_cpos[e];
+                if (cp >= 0 && (uint32_t)(e % CS) == rank) {
+                  const int k = sl_row[e];
+                  GT *dst = cache + (size_t)cp * npad;
+                  // 8 independent gathers in flight per thread (a plain loop would serialise load -> store)
+                  for (int p0f = tid; p0f < (int)npad; p0f += NT * 8) {
+                    int it[8];
+                    GT v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                      const int p = p0f + u * NT;
+                      it[u] = p < na ? act[p] : -1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) v[u] = it[u] >= 0 ? __ldg(G + gram_off(nr, k, it[u])) : (GT)0;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                      const int p = p0f + u * NT;
+                      if (p < (int)npad) __stcg(dst + p, v[u]);
+                    }
+                  }
+                }
+              }
+              __threadfence();
+              __syncthreads();
+              asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+            }
+          }
         }
         // ---- end of sweep: stop rule (cd.c:135-138)
         if (warp == 0) {
@@ -414,7 +493,7 @@ __global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, 
         const int e = cb * 32 + lane;
         const int col = sl_row[e < len ? e : 0];
         const double vk = e < len ? sl_val[e] : 0.0;
-        const double s = gram_gather_sum<GT>(G + gram_off(nr, 0, col), sl_row, sl_val, len, warp, NW);
+        const double s = gram_gather_sum<GT, false>(G + gram_off(nr, 0, col), sl_row, sl_val, len, warp, NW);
         hh = fma(vk, s, hh);
       }
     }

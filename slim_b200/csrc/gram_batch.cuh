@@ -311,7 +311,9 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
       constexpr uint32_t kRowBytes = (uint32_t)(kGramPW * sizeof(GT));  // one row of the panel
       constexpr uint32_t kSlotG = GS * 32 * LB, kSlotV = GS * T * 8;     // ring bytes per group
       const bool vlane = lane < T;
-      auto issue = [&](int g) {
+      // `slot` is a compile-time constant at every call site (the main loop is unrolled over the ring),
+      // so all shared-memory addresses are base + immediate
+      auto issue = [&](int g, const int slot) {
         if (g < ngr) {
           const int k = g / GPC, i0 = (g % GPC) * GS;
           const int c = first + k * stride;
@@ -320,7 +322,6 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
             const int e = (c + stride) * 32 + lane;  // rows of my next chunk, one chunk ahead
             row_nxt = e < len ? sl_row[e] : 0;
           }
-          const int slot = g % NG;
           const uint32_t gd = g_base + (uint32_t)slot * kSlotG;
           const uint32_t vd = v_base + (uint32_t)slot * kSlotV;
           const char *vs = v_src0 + (size_t)(c * 32 + i0) * (T * 8);
@@ -338,36 +339,43 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      auto consume_entry = [&](int se) {
+      const GT *const ring_g = &ring.g[0][lane][0];  // this lane's V elements of ring entry 0
+      const double *const ring_v = &ring.v[0][0][0];
+      auto consume_entry = [&](const int se) {  // se: compile-time ring entry
         GT gv[V];
 #pragma unroll
-        for (int v = 0; v < V; v++) gv[v] = ring.g[se][lane][v];
+        for (int v = 0; v < V; v++) gv[v] = ring_g[se * 32 * V + v];
 #pragma unroll
         for (int t = 0; t < T; t++) {
-          const double val = ring.v[se][0][t];
+          const double val = ring_v[se * T + t];
 #pragma unroll
           for (int v = 0; v < V; v++) acc[t][v] = fma(val, (double)gv[v], acc[t][v]);
         }
       };
 #pragma unroll
-      for (int p = 0; p < NG - 1; p++) issue(p);
+      for (int p = 0; p < NG - 1; p++) issue(p, p);
       int e0 = first * 32;  // first entry of group g
-      for (int g = 0; g < ngr; g++) {
-        issue(g + NG - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(NG - 1) : "memory");
-        __syncwarp();
-        const int slot = g % NG;
-        if (e0 + GS <= len) {  // whole group valid (warp-uniform): no per-entry tests
+      for (int gb = 0; gb < ngr; gb += NG) {
 #pragma unroll
-          for (int u = 0; u < GS; u++) consume_entry(slot * GS + u);
-        } else {
+        for (int sidx = 0; sidx < NG; sidx++) {
+          const int g = gb + sidx;
+          if (g < ngr) {  // warp-uniform
+            issue(g + NG - 1, (sidx + NG - 1) % NG);
+            asm volatile("cp.async.wait_group %0;" ::"n"(NG - 1) : "memory");
+            __syncwarp();
+            if (e0 + GS <= len) {  // whole group valid (warp-uniform): no per-entry tests
 #pragma unroll
-          for (int u = 0; u < GS; u++)
-            if (e0 + u < len) consume_entry(slot * GS + u);
+              for (int u = 0; u < GS; u++) consume_entry(sidx * GS + u);
+            } else {
+#pragma unroll
+              for (int u = 0; u < GS; u++)
+                if (e0 + u < len) consume_entry(sidx * GS + u);
+            }
+            __syncwarp();
+            e0 += GS;
+            if ((g + 1) % GPC == 0) e0 += (stride - 1) * 32;  // next chunk of this warp
+          }
         }
-        __syncwarp();
-        e0 += GS;
-        if ((g + 1) % GPC == 0) e0 += (stride - 1) * 32;  // next chunk of this warp
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();

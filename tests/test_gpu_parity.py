@@ -383,6 +383,26 @@ def test_gram_and_user_space_kernels_agree(lib, monkeypatch):
     assert np.allclose(out["1"][1]["objval"], out["0"][1]["objval"], rtol=1e-9)
 
 
+@pytest.mark.parametrize("cache_mb", ["0", "1", "1024"])
+def test_gram_row_cache(lib, ours, oracle, monkeypatch, cache_mb):
+    # the one-target clusters cache each nonzero coordinate's Gram row restricted to the active set: off, too
+    # small for all rows (1 MB per cluster: mixed cached / uncached entries) and large enough for everything
+    monkeypatch.setenv("SLIMB200_GRAM_CACHE_MB", cache_mb)
+    monkeypatch.setenv("SLIMB200_GRAM_HEAVY", "0")
+    monkeypatch.setenv("SLIMB200_GRAM_BATCH", "1000000000")
+    from slim_b200 import Staged, learn_columns
+
+    rp, ri, rv = st.synth_zipf(20000, 2000, 50, seed=42)
+    cols = np.arange(0, 2000, 9, dtype=np.int32)
+    with Staged(rp, ri, rv) as s:
+        r = learn_columns(s, dict(niters=50), cols=cols)
+        got, stats = r.to_host(), r.stats()
+    ref = oracle.learn(rp, ri, rv, niters=50, cols=cols, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
+    assert np.array_equal(stats["niters"], ref["stats"]["niters"])
+    _check_close(got, ref, tol=1e-6)
+    assert np.allclose(stats["objval"], ref["stats"]["objval"], rtol=1e-9)
+
+
 # ---- batched heavy-target kernel (slim_b200/csrc/gram_batch.cuh): 8 targets per cluster, item-space blocks ----
 
 @pytest.mark.parametrize("bcs", ["1", "4", "8", "16"])
