@@ -2958,9 +2958,9 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     };
     std::vector<GramClass> classes;
     if (use_gram) {
-      int gram_cs = env_int("SLIMB200_GRAM_CS", 8);
-      if (gram_cs != 1 && gram_cs != 2 && gram_cs != 4 && gram_cs != 8 && gram_cs != 16) gram_cs = 8;
-      const int gram_heavy = env_int("SLIMB200_GRAM_HEAVY", 600);
+      int gram_cs = env_int("SLIMB200_GRAM_CS", 4);
+      if (gram_cs != 1 && gram_cs != 2 && gram_cs != 4 && gram_cs != 8 && gram_cs != 16) gram_cs = 4;
+      const int gram_heavy = env_int("SLIMB200_GRAM_HEAVY", 2000);
       // measured on C4 (profiles/r01_gram_class_routing.txt): below ~30K nonzeros a batch of 8 targets costs more
       // SM-seconds than eight one-target clusters (the union nonzero list is much longer than each target's own and
       // the item-space blocks cover inactive coordinates), so by default the two batch classes coincide

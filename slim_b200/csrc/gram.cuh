@@ -203,7 +203,7 @@ __device__ __forceinline__ double gram_gather_sum(const GT *__restrict__ Gcol, c
 }
 
 template <typename GT, int CS>
-__global__ void __launch_bounds__(kGramNT, 3) cd_gram_kernel(const SolveArgs a, const GramArgs ga) {
+__global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, const GramArgs ga) {
   constexpr int NT = kGramNT, NW = kGramNW;
   __shared__ GramSmem<CS> sm;
   __shared__ GT s_gbb[32][33];

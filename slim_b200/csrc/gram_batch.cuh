@@ -307,12 +307,17 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
       }
       // loop-invariant pieces of the addresses, kept in registers (the compiler otherwise rebuilds them per entry)
       const char *const g_src0 = reinterpret_cast<const char *>(Gblk);
-      const char *const v_src0 = reinterpret_cast<const char *>(slv + lane);
       constexpr uint32_t kRowBytes = (uint32_t)(kGramPW * sizeof(GT));  // one row of the panel
       constexpr uint32_t kSlotG = GS * 32 * LB, kSlotV = GS * T * 8;     // ring bytes per group
-      const bool vlane = lane < T;
       // `slot` is a compile-time constant at every call site (the main loop is unrolled over the ring),
-      // so all shared-memory addresses are base + immediate
+      // so all shared-memory addresses are base + immediate.  Per entry: one shuffle (row id), one
+      // mad.wide (row * row bytes + panel base) and one LDGSTS; the 8 x T values of a whole group are
+      // contiguous in the list (512 B) and travel with ONE 16-byte cp.async per lane.
+      unsigned long long g_src_u64 = reinterpret_cast<unsigned long long>(g_src0);
+      asm volatile("" : "+l"(g_src_u64));  // keep the panel base in registers (do not rebuild it per entry)
+      static_assert(GS * T * 8 == 32 * 16, "one 16-byte cp.async per lane moves the values of a group");
+      const char *const v_grp0 = reinterpret_cast<const char *>(slv) + (size_t)lane * 16;
+      const uint32_t v_base16 = smem_u32(&ring.v[0][0][0]) + (uint32_t)lane * 16u;
       auto issue = [&](int g, const int slot) {
         if (g < ngr) {
           const int k = g / GPC, i0 = (g % GPC) * GS;
@@ -323,18 +328,18 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
             row_nxt = e < len ? sl_row[e] : 0;
           }
           const uint32_t gd = g_base + (uint32_t)slot * kSlotG;
-          const uint32_t vd = v_base + (uint32_t)slot * kSlotV;
-          const char *vs = v_src0 + (size_t)(c * 32 + i0) * (T * 8);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(v_base16 + (uint32_t)slot * kSlotV),
+                       "l"(v_grp0 + (size_t)(c * 32 + i0) * (T * 8))
+                       : "memory");
 #pragma unroll
           for (int u = 0; u < GS; u++) {
             const uint32_t r = (uint32_t)__shfl_sync(0xffffffffu, row_cur, i0 + u);
-            const char *src = g_src0 + (size_t)r * kRowBytes;
+            unsigned long long src;
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(src) : "r"(r), "r"(kRowBytes), "l"(g_src_u64));
             if (LB == 8)
               asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(gd + (uint32_t)(u * 32 * LB)), "l"(src) : "memory");
             else
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gd + (uint32_t)(u * 32 * LB)), "l"(src) : "memory");
-            if (vlane)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(vd + (uint32_t)(u * T * 8)), "l"(vs + u * T * 8) : "memory");
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
