@@ -553,6 +553,16 @@ int32_t Py_SLIM_Predict_1vsk(int32_t nrcmds, int32_t nnegs, slim_t *slimhandle, 
 int32_t Py_SLIM_Predict(int32_t nrcmds, slim_t *slimhandle, slim_t *trnhandle, int32_t *output, float *scores) {
   const CsrHandle *w = static_cast<const CsrHandle *>(slimhandle);
   const CsrHandle *t = static_cast<const CsrHandle *>(trnhandle);
+  if (!w || !t || !w->rowptr || !t->rowptr) return SLIM_ERROR;
+  // batched on the GPU (predict.cuh): one CTA per user, lists and scores bit-identical to recommend() below.
+  // SLIMB200_PREDICT_HOST=1 (or no usable device) keeps the per-user host loop of the reference.
+  const char *force_host = getenv("SLIMB200_PREDICT_HOST");
+  if (nrcmds > 0 && t->nrows > 0 && device_count() > 0 && !(force_host && atoi(force_host))) {
+    const int rc = predict_topn(env_device(), w->nrows, w->ncols, w->rowptr, w->rowind, w->rowval, t->nrows, t->rowptr,
+                                t->rowind, t->rowval, nrcmds, output, scores, nullptr, nullptr);
+    if (rc == kOk) return SLIM_OK;
+    fprintf(stderr, "[slim-b200] GPU top-N failed (%s): using the host loop\n", last_error());
+  }
   std::vector<int32_t> rids((size_t)std::max(nrcmds, 1));
   std::vector<float> rsc((size_t)std::max(nrcmds, 1));
   int32_t nvalid = 0;

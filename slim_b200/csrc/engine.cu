@@ -2436,6 +2436,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
 
 #include "gram.cuh"
 #include "gram_batch.cuh"
+#include "predict.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K0g host side: decide whether G fits, pick its element type, build it (part of staging).
@@ -3398,6 +3399,102 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
   }
   free_result(res);
   return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the batched top-N (predict.cuh)
+// ------------------------------------------------------------------------------------------------
+int predict_topn(int device, int32_t wrows, int32_t wcols, const ssize_t *wrowptr, const int32_t *wrowind,
+                 const float *wrowval, int32_t nusers, const ssize_t *urowptr, const int32_t *urowind,
+                 const float *urowval, int32_t nrcmds, int32_t *out_ids, float *out_scores, int32_t *out_counts,
+                 double *kernel_ms) {
+  try {
+    if (device < 0 || device >= device_count()) throw EngineError(kErr, "predict_topn: no usable CUDA device");
+    if (wrows < 0 || wcols < 0 || nusers < 0 || nrcmds <= 0 || !wrowptr || !urowptr)
+      throw EngineError(kErrInput, "predict_topn: bad arguments");
+    DeviceGuard guard(device);
+    (void)cudaGetLastError();
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int64_t wnnz = wrowptr[wrows], unnz = urowptr[nusers];
+    static_assert(sizeof(ssize_t) == sizeof(int64_t), "LP64 only");
+    DevBuf<int64_t> d_wp, d_up;
+    DevBuf<int32_t> d_wi, d_ui, d_mark, d_cand, d_oid, d_cnt;
+    DevBuf<float> d_wv, d_uv, d_score, d_osc;
+    d_wp.alloc((size_t)wrows + 1);
+    d_up.alloc((size_t)nusers + 1);
+    d_wi.alloc(wnnz);
+    d_wv.alloc(wnnz);
+    d_ui.alloc(unnz);
+    if (urowval) d_uv.alloc(unnz);
+    CK(cudaMemcpy(d_wp.p, wrowptr, sizeof(int64_t) * ((size_t)wrows + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_up.p, urowptr, sizeof(int64_t) * ((size_t)nusers + 1), cudaMemcpyHostToDevice));
+    if (wnnz > 0) {
+      CK(cudaMemcpy(d_wi.p, wrowind, sizeof(int32_t) * wnnz, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d_wv.p, wrowval, sizeof(float) * wnnz, cudaMemcpyHostToDevice));
+    }
+    if (unnz > 0) {
+      CK(cudaMemcpy(d_ui.p, urowind, sizeof(int32_t) * unnz, cudaMemcpyHostToDevice));
+      if (urowval) CK(cudaMemcpy(d_uv.p, urowval, sizeof(float) * unnz, cudaMemcpyHostToDevice));
+    }
+    const size_t nout = (size_t)nusers * nrcmds;
+    d_oid.alloc(nout);
+    d_osc.alloc(nout);
+    d_cnt.alloc_zero(nusers, nullptr);
+    if (nout > 0) {  // rows shorter than nrcmds keep the caller's content
+      CK(cudaMemcpy(d_oid.p, out_ids, sizeof(int32_t) * nout, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d_osc.p, out_scores, sizeof(float) * nout, cudaMemcpyHostToDevice));
+    }
+    const int grid = std::max(1, std::min(nusers, prop.multiProcessorCount * 8));
+    const size_t stride = ((size_t)std::max(wcols, 1) + 31) & ~size_t(31);
+    d_score.alloc_zero((size_t)grid * stride, nullptr);
+    d_mark.alloc_zero((size_t)grid * stride, nullptr);
+    d_cand.alloc((size_t)grid * stride);
+    PredictArgs pa{};
+    pa.nusers = nusers;
+    pa.wrows = wrows;
+    pa.wcols = wcols;
+    pa.nrcmds = nrcmds;
+    pa.wrowptr = d_wp.p;
+    pa.wrowind = d_wi.p;
+    pa.wrowval = d_wv.p;
+    pa.urowptr = d_up.p;
+    pa.urowind = d_ui.p;
+    pa.urowval = urowval ? d_uv.p : nullptr;
+    pa.score = d_score.p;
+    pa.mark = d_mark.p;
+    pa.cand = d_cand.p;
+    pa.stride = stride;
+    pa.out_ids = d_oid.p;
+    pa.out_scores = d_osc.p;
+    pa.out_counts = d_cnt.p;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, nullptr));
+    if (nusers > 0) predict_topn_kernel<<<grid, kPredNT>>>(pa);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, nullptr));
+    CK(cudaDeviceSynchronize());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (kernel_ms) *kernel_ms = ms;
+    if (nout > 0) {
+      CK(cudaMemcpy(out_ids, d_oid.p, sizeof(int32_t) * nout, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(out_scores, d_osc.p, sizeof(float) * nout, cudaMemcpyDeviceToHost));
+    }
+    if (out_counts && nusers > 0)
+      CK(cudaMemcpy(out_counts, d_cnt.p, sizeof(int32_t) * nusers, cudaMemcpyDeviceToHost));
+    return kOk;
+  } catch (const EngineError &e) {
+    g_last_error = e.what();
+    return e.status;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    return kErrMemory;
+  }
 }
 
 }  // namespace slimb200

@@ -71,6 +71,16 @@ int result_to_host(const Result *r, int64_t *colptr, int32_t *colind, float *col
 // Same, into caller-owned DEVICE buffers on the matrix's device (counts int32[nsel]).
 int result_to_device(const Result *r, int32_t *d_counts, int32_t *d_colind, float *d_colval);
 
+// Batched top-N for every row of a user-history matrix on the GPU: the loop of Py_SLIM_Predict (reference
+// src/libslim/pyapi.c:530-563) around GetRecommendations (src/libslim/predict.c:15-71).  Host arrays in and
+// out; out_ids / out_scores are [nusers][nrcmds] and only the first out_counts[u] entries of a row are
+// written (the arrays are read first, so the rest keeps the caller's content).  Lists and scores are
+// bit-identical to the host restatement in api.cpp.
+int predict_topn(int device, int32_t wrows, int32_t wcols, const ssize_t *wrowptr, const int32_t *wrowind,
+                 const float *wrowval, int32_t nusers, const ssize_t *urowptr, const int32_t *urowind,
+                 const float *urowval, int32_t nrcmds, int32_t *out_ids, float *out_scores, int32_t *out_counts,
+                 double *kernel_ms);
+
 int device_count();
 const char *last_error();
 

@@ -543,6 +543,28 @@ def test_python_mirror_train_predict(lib, ml100k):
     assert abs(model.to_csr().nnz - 65909) <= 2
 
 
+def test_gpu_topn_matches_host_loop(lib, ours, monkeypatch):
+    # Py_SLIM_Predict: the batched GPU top-N (predict.cuh) against the per-user host loop of the reference
+    # restatement -- identical lists AND bit-identical float scores, short lists keep the caller's filler
+    from slim_b200 import SLIM, SLIMatrix
+    import scipy.sparse as sp
+
+    for name, nr in (("ml100k", 10), ("automotive", 25)):
+        g = st.load_golden(name)
+        shape = (len(g["trn_rowptr"]) - 1, int(g["trn_rowind"].max()) + 1)
+        trn = SLIMatrix(sp.csr_matrix((g["trn_rowval"], g["trn_rowind"], g["trn_rowptr"]), shape=shape))
+        model = SLIM()
+        model.train({"algo": "cd", "l1r": 1.0, "l2r": 1.0, "niters": 30}, trn)
+        monkeypatch.setenv("SLIMB200_PREDICT_HOST", "1")
+        host_ids, host_sc = model.predict(trn, nrcmds=nr, returnscores=True)
+        monkeypatch.setenv("SLIMB200_PREDICT_HOST", "0")
+        gpu_ids, gpu_sc = model.predict(trn, nrcmds=nr, returnscores=True)
+        for u in range(shape[0]):
+            assert np.array_equal(np.asarray(host_ids[u]), np.asarray(gpu_ids[u])), (name, u)
+            assert np.array_equal(np.asarray(host_sc[u], np.float32).view(np.uint32),
+                                  np.asarray(gpu_sc[u], np.float32).view(np.uint32)), (name, u)
+
+
 def test_model_selection_keeps_matrix_resident(lib, automotive, capfd):
     # Py_SLIM_Mselect (reference pyapi.c:214-412): (l1, l2) grid with warm starts; here R is staged once
     from slim_b200 import SLIM, SLIMatrix
