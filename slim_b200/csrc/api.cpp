@@ -613,6 +613,8 @@ int32_t Py_SLIM_Mselect(slim_t *trnhandle, slim_t *tsthandle, int32_t *ioptions,
   CsrHandle *model = nullptr;
   *bestHRHR = *bestARHR = *bestHRAR = *bestARAR = 0.0;
   int32_t rc = SLIM_OK;
+  std::vector<int32_t> all_ids, all_cnt;
+  std::vector<float> all_sc;
   for (int32_t i1 = 0; i1 < nl1 && rc == SLIM_OK; i1++) {
     for (int32_t i2 = 0; i2 < nl2; i2++) {
       doptions[SLIM_OPTION_L1R] = arrayl1[i1];
@@ -647,11 +649,31 @@ int32_t Py_SLIM_Mselect(slim_t *trnhandle, slim_t *tsthandle, int32_t *ioptions,
       std::fill(rmarker.begin(), rmarker.end(), -1);
       double hr[3] = {0, 0, 0}, arhr = 0.0;
       int32_t nvalid = 0, nvalid_head = 0, nvalid_tail = 0;
+      // top-N lists of all users in one batched GPU call (predict.cuh); per-user host loop as the fallback
+      bool gpu_lists = false;
+      {
+        const char *force_host = getenv("SLIMB200_PREDICT_HOST");
+        if (p.nrcmds > 0 && trn->nrows > 0 && device_count() > 0 && !(force_host && atoi(force_host))) {
+          all_ids.assign((size_t)trn->nrows * p.nrcmds, -1);
+          all_sc.assign((size_t)trn->nrows * p.nrcmds, 0.f);
+          all_cnt.assign((size_t)trn->nrows, 0);
+          gpu_lists = predict_topn(env_device(), model->nrows, model->ncols, model->rowptr, model->rowind,
+                                   model->rowval, trn->nrows, trn->rowptr, trn->rowind, trn->rowval, p.nrcmds,
+                                   all_ids.data(), all_sc.data(), all_cnt.data(), nullptr) == kOk;
+        }
+      }
       for (int32_t u = 0; u < trn->nrows; u++) {
         if (u >= tst->nrows || tst->rowptr[u + 1] - tst->rowptr[u] < 1) continue;
         const ssize_t a = trn->rowptr[u], b = trn->rowptr[u + 1];
-        const int32_t n = recommend(model, (int32_t)(b - a), trn->rowind + a, trn->rowval ? trn->rowval + a : nullptr,
-                                    p.nrcmds, rids.data(), rsc.data());
+        int32_t n;
+        const int32_t *rids_u = rids.data();
+        if (gpu_lists) {
+          n = all_cnt[u];
+          rids_u = all_ids.data() + (size_t)u * p.nrcmds;
+        } else {
+          n = recommend(model, (int32_t)(b - a), trn->rowind + a, trn->rowval ? trn->rowval + a : nullptr, p.nrcmds,
+                        rids.data(), rsc.data());
+        }
         nvalid += n >= 0 ? 1 : 0;
         int is_tail = 0, is_head = 0, ntrue[2] = {0, 0}, nhits[3] = {0, 0, 0};
         double larhr = 0.0, baseline = 0.0;
@@ -664,8 +686,8 @@ int32_t Py_SLIM_Mselect(slim_t *trnhandle, slim_t *tsthandle, int32_t *ioptions,
         nvalid_tail += is_tail;
         nvalid_head += is_head;
         for (int32_t r = 0; r < n; r++)
-          if (rmarker[rids[r]] == u) {
-            nhits[fm[rids[r]]]++;
+          if (rmarker[rids_u[r]] == u) {
+            nhits[fm[rids_u[r]]]++;
             nhits[2]++;
             larhr += 1.0 / (1.0 + r);
           }
