@@ -1,5 +1,5 @@
 import os, sys, numpy as np, torch, time
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import pathlib; ROOT = pathlib.Path(__file__).resolve().parent.parent; sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / 'tests'))
 from slim_b200 import Staged, learn_columns
 from slim_b200.synth import zipf_csr, stratified_columns
 rp, ri, rv = zipf_csr(1_000_000, 100_000, 100, device='cuda')

@@ -1,5 +1,5 @@
 import os, sys, time, numpy as np, scipy.sparse as sp
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import pathlib; ROOT = pathlib.Path(__file__).resolve().parent.parent; sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / 'tests'))
 import slimtest as st
 from slim_b200 import SLIM, SLIMatrix
 rp, ri, rv = st.synth_zipf(100000, 10000, 50, seed=7)
