@@ -269,7 +269,7 @@ def main():
     colcnt = np.diff(staged.csc()["colptr"]) if staged.nnz < 5_000_000 else \
         torch.bincount(ri_d.to(torch.int64), minlength=staged.ncols).cpu().numpy()
     params = dict(PARAMS, l1r=args.l1r)
-    ncs_total = args.cols_per_step * world
+    ncs_total = min(args.cols_per_step * world, int(staged.ncols))  # never more targets than there are columns
 
     def barrier():
         torch.cuda.synchronize()
