@@ -405,7 +405,9 @@ def main():
         line = dict(base, value=value, ms_per_step=1e3 * wall / args.steps,
                     config={"workload": wl_name, "cols_per_step_per_gpu": args.cols_per_step,
                             "parallelism": f"column-sharded x{world}, R replicated",
-                            "l2_policy": "inputs (2 GB CSR+CSC) >> 126 MB L2; different columns every step",
+                            "l2_policy": ("inputs >> 126 MB L2 (the solver streams the 40 GB Gram matrix, ~54 TB of DRAM traffic per "
+                                          "step); different columns every step" if gram_eb else
+                                          "inputs (2 GB CSR+CSC) >> 126 MB L2; different columns every step"),
                             "datagen_s": round(gen_s, 2), "stage_ms": round(staged.stage_ms, 2),
                             "gram": {"elem_bytes": gram_eb, "build_ms": round(gram_ms, 1),
                                      "GB": round(gram_eb * staged.ncols * staged.ncols / 1e9, 2)}},
