@@ -5,6 +5,9 @@
 //   EstimateModelCD        reference src/libslim/estimate.c:328-558 -> learn()        (cd_solve_kernel)
 //   CoordinateDescent      reference src/libslim/cd.c:101-142       -> the sweep loop inside cd_solve_kernel
 //   SaveModel              reference src/libslim/estimate.c:570-593 -> gather_columns_kernel + host assembly (api.cpp)
+// The default solver works in GRAM space (gram.cuh, gram_batch.cuh: G = R^T R staged once, no pass over R per
+// target); the user-space kernels in this file are the path when G does not fit in HBM.  predict.cuh holds the
+// batched top-N (reference src/libslim/predict.c).
 //
 // Data layout in HBM:
 //   CSR   rowptr int64[nrows+1], rowind int32[nnz], rowval fp32[nnz] (absent for all-ones input)
