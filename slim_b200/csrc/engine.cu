@@ -99,6 +99,20 @@ struct DeviceGuard {
   }
 };
 
+struct EventPair {  // two timing events, destroyed on every exit path
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventPair() {
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+  }
+  EventPair(const EventPair &) = delete;
+  EventPair &operator=(const EventPair &) = delete;
+  ~EventPair() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
+
 int device_count() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -2488,15 +2502,12 @@ static void build_gram(Matrix *m) {
       fprintf(stderr, "[slim-b200] Gram matrix (%.1f GB) does not fit: user-space kernels will be used\n", bytes / 1e9);
     return;
   }
-  cudaEvent_t g0, g1;
-  CK(cudaEventCreate(&g0));
-  CK(cudaEventCreate(&g1));
+  EventPair ev;
+  cudaEvent_t g0 = ev.a, g1 = ev.b;
   CK(cudaEventRecord(g0, s));
   if (cudaMalloc(&m->d_gram, bytes) != cudaSuccess) {  // not fatal: fall back to the user-space kernels
     (void)cudaGetLastError();
     m->d_gram = nullptr;
-    cudaEventDestroy(g0);
-    cudaEventDestroy(g1);
     return;
   }
   CK(cudaMemsetAsync(m->d_gram, 0, bytes, s));
@@ -2541,8 +2552,6 @@ static void build_gram(Matrix *m) {
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, g0, g1));
   m->gram_ms = ms;
-  cudaEventDestroy(g0);
-  cudaEventDestroy(g1);
   if (env_int("SLIMB200_VERBOSE", 0))
     fprintf(stderr, "[slim-b200] Gram matrix: %d x %zu %s, %.2f GB, %d work items, built in %.1f ms\n", ncols, ld,
             exact32 ? "fp32 (exact)" : "fp64", bytes / 1e9, nwork, ms);
@@ -3471,9 +3480,8 @@ int predict_topn(int device, int32_t wrows, int32_t wcols, const ssize_t *wrowpt
     pa.out_ids = d_oid.p;
     pa.out_scores = d_osc.p;
     pa.out_counts = d_cnt.p;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    EventPair ev;
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     CK(cudaEventRecord(e0, nullptr));
     if (nusers > 0) predict_topn_kernel<<<grid, kPredNT>>>(pa);
     CK(cudaGetLastError());
@@ -3481,8 +3489,6 @@ int predict_topn(int device, int32_t wrows, int32_t wcols, const ssize_t *wrowpt
     CK(cudaDeviceSynchronize());
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (kernel_ms) *kernel_ms = ms;
     if (nout > 0) {
       CK(cudaMemcpy(out_ids, d_oid.p, sizeof(int32_t) * nout, cudaMemcpyDeviceToHost));
