@@ -11,8 +11,10 @@ import slimtest as st
 EPS = 1e-7  # EPSILON, reference src/libslim/def.h:14
 
 
-def gram_space_cd(G, cnorm, j, l1r, l2r, opttol, maxniters, colcnt_j, block=32):
-    """Column j of W by the procedure of cd_gram_kernel (internal item order = order of G)."""
+def gram_space_cd(G, cnorm, j, l1r, l2r, opttol, maxniters, colcnt_j, block=32, item_space=False):
+    """Column j of W by the procedure of cd_gram_kernel (internal item order = order of G): blocks of `block`
+    consecutive ACTIVE coordinates; item_space=True: blocks of `block` consecutive ITEM ids with the inactive ones
+    masked out, the blocking of cd_gram_batch_kernel (64 items per block)."""
     aty_all = G[j].copy()
     act = np.nonzero((aty_all > l1r) & (np.arange(len(aty_all)) != j))[0]
     na = len(act)
@@ -29,8 +31,13 @@ def gram_space_cd(G, cnorm, j, l1r, l2r, opttol, maxniters, colcnt_j, block=32):
     t = 0
     while t < maxit and not done:
         dl = 0.0
-        for p0 in range(0, na, block):
-            sl = slice(p0, min(na, p0 + block))
+        if item_space:  # [start, end) positions of the actives inside every block of `block` item ids
+            edges = np.searchsorted(act, np.arange(0, G.shape[0] + block, block))
+            spans = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        else:
+            spans = [(p0, min(na, p0 + block)) for p0 in range(0, na, block)]
+        for p0, p1 in spans:
+            sl = slice(p0, p1)
             xin = np.where(np.abs(x) > EPS, x, 0.0)  # AddSpVec's EPSILON rule (cd.c:27)
             ipf = GA[sl] @ xin                      # the gather over the nonzero list
             xb = x[sl].copy()
@@ -59,7 +66,12 @@ def gram_space_cd(G, cnorm, j, l1r, l2r, opttol, maxniters, colcnt_j, block=32):
     return act, x, niters
 
 
-def test_gram_space_sweeps_equal_user_space_sweeps(oracle, ml100k):
+import pytest
+
+
+@pytest.mark.parametrize("blocking", [dict(block=32), dict(block=64, item_space=True)],
+                         ids=["position-blocks-32", "item-blocks-64"])
+def test_gram_space_sweeps_equal_user_space_sweeps(oracle, ml100k, blocking):
     g = ml100k
     rp, ri, rv = g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"]
     nitems = int(ri.max()) + 1
@@ -78,7 +90,7 @@ def test_gram_space_sweeps_equal_user_space_sweeps(oracle, ml100k):
         rank[inv] = np.arange(nitems)
         for q, j in enumerate(cols):
             act, x, niters = gram_space_cd(G, cnorm, int(rank[j]), kw["l1r"], kw["l2r"], kw["opttol"], kw["niters"],
-                                           int(cnt[j]))
+                                           int(cnt[j]), **blocking)
             keep = np.abs(x) > EPS
             got = dict(zip(inv[act[keep]].tolist(), x[keep].astype(np.float32).tolist()))
             a, b = ref["colptr"][q], ref["colptr"][q + 1]
