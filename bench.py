@@ -168,7 +168,7 @@ def _capture_stdout(fn):
         return out, tf.read().decode(errors="replace")
 
 
-def reference_step(ref, rp, ri, rv, cols, nthreads, l1r):
+def reference_step(ref, rp, ri, rv, cols, nthreads, l1r, keep_w=None):
     """One SLIM_Learn of the reference restricted to `cols` (mask exported by libslim_ref_cols.so).
     Returns (seconds by the library's Learn timer, wall seconds, nnz of the solved columns)."""
     import slimtest as st
@@ -188,10 +188,36 @@ def reference_step(ref, rp, ri, rv, cols, nthreads, l1r):
     ref.free(h)
     m = re.search(r"Learn:\s+([0-9.]+)", text)
     learn_s = float(m.group(1)) if m else wall
+    if keep_w is not None:  # CSC of the solved columns, in the order of `cols` (parity_check)
+        cp = mv["colptr"]
+        seg = [np.arange(cp[j], cp[j + 1]) for j in cols]
+        idx = np.concatenate(seg) if seg else np.zeros(0, np.int64)
+        keep_w.update(cols=np.asarray(cols, np.int32), colptr=np.concatenate([[0], np.cumsum([len(x) for x in seg])]),
+                      colind=mv["colind"][idx], colval=mv["colval"][idx])
     return learn_s, wall, int(np.diff(mv["colptr"])[cols].sum())
 
 
-def run_reference(args, rp, ri, rv, colcnt, steps, warmup):
+def host_objective(rp, ri, rv, cols, w, l1r, l2r):
+    """Objective of estimate.c:477-489, 1/2 |r_j - R w_j|^2 + l2r/2 |w_j|^2 + l1r |w_j|_1, evaluated on the host
+    in fp64 from a CSC of W (dict cols/colptr/colind/colval) -- the same function for both arms."""
+    import scipy.sparse as sp
+
+    nu, ni = len(rp) - 1, int(ri.max()) + 1
+    R = sp.csr_matrix((rv.astype(np.float64), ri, rp), shape=(nu, ni))
+    out = np.zeros(len(cols))
+    for k0 in range(0, len(cols), 16):  # 16 columns of yhat at a time (nusers x 16 doubles)
+        ks = range(k0, min(len(cols), k0 + 16))
+        W = np.zeros((ni, len(ks)))
+        for c, k in enumerate(ks):
+            a, b = int(w["colptr"][k]), int(w["colptr"][k + 1])
+            W[w["colind"][a:b], c] = w["colval"][a:b]
+        Y = R @ W
+        T = R[:, [int(cols[k]) for k in ks]].toarray()
+        out[k0:k0 + len(ks)] = (0.5 * ((T - Y) ** 2).sum(0) + 0.5 * l2r * (W ** 2).sum(0) + l1r * np.abs(W).sum(0))
+    return out
+
+
+def run_reference(args, rp, ri, rv, colcnt, steps, warmup, keep_w=None):
     import slimtest as st
 
     if not st.ref_lib_path(cols=True).exists():
@@ -204,7 +230,7 @@ def run_reference(args, rp, ri, rv, colcnt, steps, warmup):
     times, walls = [], []
     for s in range(warmup + steps):
         cols = stratified_columns(colcnt, ncs, offset=s)
-        learn_s, wall, _ = reference_step(ref, rp, ri, rv, cols, nthreads, args.l1r)
+        learn_s, wall, _ = reference_step(ref, rp, ri, rv, cols, nthreads, args.l1r, keep_w)
         if s >= warmup:
             times.append(learn_s)
             walls.append(wall)
@@ -388,15 +414,38 @@ def main():
                "api": "SLIMB200_Stage + SLIMB200_LearnColumns + SLIMB200_ResultToHost (host buffers)"}
 
     cpu_baseline = None
+    parity_check = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             rp_h, ri_h, rv_h = rp_d.cpu().numpy(), ri_d.cpu().numpy(), rv_d.cpu().numpy()
-            r = run_reference(args, rp_h, ri_h, rv_h, colcnt, steps=1, warmup=0)
+            ref_w = {}
+            r = run_reference(args, rp_h, ri_h, rv_h, colcnt, steps=1, warmup=0, keep_w=ref_w)
             if r is not None:
                 cpu_baseline = {"value": r["value"], "unit": "columns/s", "cores": r["cores"], "kind": "reference",
                                 "sample": f"{r['cols_per_step']} stratified target columns of the same R, one "
                                           f"SLIM_Learn of oracle/_ref (column-mask build), library Learn timer "
                                           f"{r['ms_per_step'] / 1e3:.1f} s"}
+                # parity at the benchmarked scale: the SAME columns on the GPU, both W's scored by
+                # one host function; the reference visits coordinates in rand() order and stops at optTol / the
+                # 50-sweep cap, so the objectives (not the weights) are the comparable quantity
+                pcols = ref_w["cols"]
+                gres = learn_columns(staged, params, cols=pcols)
+                gw = dict(gres.to_host(), cols=pcols)
+                gstats = gres.stats()
+                gres.close()
+                o_ref = host_objective(rp_h, ri_h, rv_h, pcols, ref_w, args.l1r, PARAMS["l2r"])
+                o_gpu = host_objective(rp_h, ri_h, rv_h, pcols, gw, args.l1r, PARAMS["l2r"])
+                import slimtest as st_
+
+                maxd, flips = st_.compare_models(gw, ref_w)
+                parity_check = {"cols": int(len(pcols)),
+                                "max_rel_objective": float(np.max(np.abs(o_gpu - o_ref) / np.maximum(o_ref, 1e-300))),
+                                "max_rel_objective_engine_vs_host": float(np.max(
+                                    np.abs(gstats["objval"] - o_gpu) / np.maximum(o_gpu, 1e-300))),
+                                "nnz_ref": int(ref_w["colptr"][-1]), "nnz_gpu": int(gw["colptr"][-1]),
+                                "max_abs_dw": float(maxd), "support_flips": int(len(flips)),
+                                "note": "same 64 columns of the same R solved by oracle/_ref (16 threads, rand() order) "
+                                        "and by the engine; objectives of both W's from one fp64 host function"}
         except Exception as ex:  # the baseline leg must not take the bench line down
             cpu_baseline = {"value": None, "unit": "columns/s", "cores": os.cpu_count(), "kind": "reference",
                             "sample": f"failed: {ex!r}"}
@@ -411,7 +460,7 @@ def main():
                             "datagen_s": round(gen_s, 2), "stage_ms": round(staged.stage_ms, 2),
                             "gram": {"elem_bytes": gram_eb, "build_ms": round(gram_ms, 1),
                                      "GB": round(gram_eb * staged.ncols * staged.ncols / 1e9, 2)}},
-                    roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, clocks=clocks,
+                    roofline=roofline, cpu_baseline=cpu_baseline, parity_check=parity_check, e2e=e2e, clocks=clocks,
                     gpu_launches=int(launches))
         print(json.dumps(line))
     staged.close()
