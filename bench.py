@@ -18,8 +18,9 @@ reference : the UNMODIFIED reference OpenMP learner built into oracle/_ref (colu
             see oracle/Makefile), all host cores, timed by the library's own "Learn" timer.
 
 N > 1 (torchrun): every rank holds a replica of R, the step's columns are dealt across ranks, one
-NCCL all-gather assembles W at the end of every step (inside the timed region); weak scaling
-(columns per step grow with N).  One JSON line on rank 0.
+NCCL all-gather inside libslim.so (SLIMB200_AllGatherColumns) assembles W on every rank at the end
+of every step (inside the timed region of `value` AND of `e2e`); weak scaling (columns per step grow
+with N).  One JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -282,7 +283,7 @@ def main():
     import torch.distributed as dist
 
     from slim_b200 import Staged, learn_columns
-    from slim_b200.dist import all_gather_columns, shard_columns
+    from slim_b200.dist import Communicator, shard_columns
     from slim_b200.synth import stratified_columns
 
     assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device: there is no CPU fallback"
@@ -290,6 +291,7 @@ def main():
     dev = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
+    comm = Communicator(local_rank) if world > 1 else None  # NCCL communicator owned by libslim.so
     rp_d, ri_d, rv_d, gen_s = make_matrix(args.workload, dev)
     staged = Staged(rp_d, ri_d, rv_d, device=local_rank)   # inputs already resident in HBM
     colcnt = np.diff(staged.csc()["colptr"]) if staged.nnz < 5_000_000 else \
@@ -307,14 +309,14 @@ def main():
         cols = stratified_columns(colcnt, ncs_total, offset=s)
         mine = shard_columns(cols, colcnt, rank, world)
         res = learn_columns(staged, params, cols=cols[mine])
-        if world > 1:
-            counts = torch.empty(max(res.nsel, 1), dtype=torch.int32, device=dev)
-            ind = torch.empty(max(res.nnz, 1), dtype=torch.int32, device=dev)
-            val = torch.empty(max(res.nnz, 1), dtype=torch.float32, device=dev)
-            res.to_device(counts, ind, val)
-            all_gather_columns(mine, counts[:res.nsel], ind[:res.nnz], val[:res.nnz], len(cols))
+        gather_ms, gather_launches = 0.0, 0
+        if world > 1:  # ONE NCCL all-gather inside libslim.so: every rank ends up with all columns of the step in HBM
+            full = comm.all_gather_columns(res, mine, len(cols))
+            gather_ms, gather_launches = full.gather_ms, full.launches
+            full.close()
         if keep is not None:
-            keep.append((cols[mine], res.stats(), res.nnz, res.solve_ms, res.launches, res.phases()))
+            keep.append((cols[mine], res.stats(), res.nnz, res.solve_ms, res.launches + gather_launches, res.phases(),
+                         gather_ms))
         res.close()
 
     for s in range(args.warmup):
@@ -348,13 +350,14 @@ def main():
         with open(args.dump_targets, "w") as f:
             f.write("col,c_j,nactive,rounds_per_sweep,niters,active_nnz,us_candidates,us_active_set,us_sweeps,"
                     "us_epilogue,us_per_round\n")
-            for cols, stats, wnnz, sms, nl, (ph, ng) in kept:
+            for cols, stats, wnnz, sms, nl, (ph, ng), _g in kept:
                 for k in np.argsort(-ph[:, 2]):
                     rounds = max(int(ng[k]) * max(int(min(stats["niters"][k], PARAMS["niters"])), 1), 1)
                     f.write(f"{cols[k]},{colcnt[cols[k]]},{stats['nactive'][k]},{ng[k]},{stats['niters'][k]},"
                             f"{stats['active_nnz'][k]},{ph[k,0]:.0f},{ph[k,1]:.0f},{ph[k,2]:.0f},{ph[k,3]:.0f},"
                             f"{ph[k,2] / rounds:.2f}\n")
-    for cols, stats, wnnz, sms, nl, _ph in kept:
+    allgather_ms = float(np.mean([k[6] for k in kept])) if kept else 0.0
+    for cols, stats, wnnz, sms, nl, _ph, _g in kept:
         cb, sb, ob, sw = algorithmic_bytes(colcnt, cols, stats, wnnz, PARAMS["niters"])
         cand_b, sweep_b, out_b = cand_b + cb, sweep_b + sb, out_b + ob
         solve_ms += sms
@@ -395,6 +398,10 @@ def main():
             mine = shard_columns(cols, colcnt, rank, world)
             with Staged(rp_h, ri_h, rv_h, device=local_rank) as st_:
                 res = learn_columns(st_, params, cols=cols[mine])
+                if world > 1:  # the all-gather is part of the job: every rank reads the WHOLE step's W back
+                    full = comm.all_gather_columns(res, mine, len(cols))
+                    res.close()
+                    res = full
                 w = res.to_host()
                 d2h_total += w["colptr"].nbytes + w["colind"].nbytes + w["colval"].nbytes
                 res.close()
@@ -411,7 +418,8 @@ def main():
             dist.all_reduce(ew, op=dist.ReduceOp.MAX)
         e2e = {"value": ncs_total * args.steps / float(ew.item()), "unit": "columns/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_total / max(args.steps, 1)),
-               "api": "SLIMB200_Stage + SLIMB200_LearnColumns + SLIMB200_ResultToHost (host buffers)"}
+               "api": "SLIMB200_Stage + SLIMB200_LearnColumns" + (" + SLIMB200_AllGatherColumns" if world > 1 else "") +
+                      " + SLIMB200_ResultToHost (host buffers)"}
 
     cpu_baseline = None
     parity_check = None
@@ -453,7 +461,9 @@ def main():
     if rank == 0:
         line = dict(base, value=value, ms_per_step=1e3 * wall / args.steps,
                     config={"workload": wl_name, "cols_per_step_per_gpu": args.cols_per_step,
-                            "parallelism": f"column-sharded x{world}, R replicated",
+                            "parallelism": f"column-sharded x{world}, R replicated" +
+                                           (f", one NCCL all-gather of W per step inside libslim.so ({allgather_ms:.1f} ms)"
+                                            if world > 1 else ""),
                             "l2_policy": ("inputs >> 126 MB L2 (the solver streams the 40 GB Gram matrix, ~54 TB of DRAM traffic per "
                                           "step); different columns every step" if gram_eb else
                                           "inputs (2 GB CSR+CSC) >> 126 MB L2; different columns every step"),
@@ -465,6 +475,7 @@ def main():
         print(json.dumps(line))
     staged.close()
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
     return 0
 

@@ -84,6 +84,36 @@ int32_t SLIMB200_ResultToHost(const slimb200_result_t *result, int64_t *colptr, 
 int32_t SLIMB200_ResultToDevice(const slimb200_result_t *result, int32_t *d_counts,
                                 int32_t *d_colind, float *d_colval);
 
+/* ---- multi-GPU --------------------------------------------------------------------------------
+ * The target columns are independent problems (reference src/libslim/estimate.c:402-403 is a plain parallel-for),
+ * so learning shards by column: R replicated on every GPU, every rank solves its own columns with
+ * SLIMB200_LearnColumns and ONE NCCL all-gather at the end assembles W on every rank -- the counterpart of
+ * SaveModel's concatenation of the per-column lists (estimate.c:570-588).
+ *
+ * Inside one process SLIM_Learn / Py_SLIM_Learn do all of this themselves: they use the devices named by the
+ * environment (SLIMB200_DEVICES="0,1,..", or SLIMB200_GPUS=n; default: every visible device for matrices with
+ * >= 20 M nonzeros, else one), one host thread per device, communicators created once per process.
+ * With one process per GPU (torchrun, MPI) the caller exchanges the 128-byte id of rank 0 by its own means and uses
+ * the three calls below.  NCCL is bound at run time (libnccl.so.2); without it these calls fail with SLIM_ERROR. */
+typedef struct slimb200_comm slimb200_comm_t;
+/* ncclGetUniqueId: fills 128 bytes on the calling rank (rank 0), to be sent to every other rank. */
+int32_t SLIMB200_CommUniqueId(void *id128);
+/* ncclCommInitRank on `device`; collective over the nranks callers. */
+slimb200_comm_t *SLIMB200_CommInitRank(int32_t device, int32_t nranks, int32_t rank, const void *id128,
+                                       int32_t *r_status);
+void SLIMB200_CommFree(slimb200_comm_t **comm);
+/* Collective.  `local` holds the columns this rank solved; positions[k] (host, int32[nsel of local]) is the index of
+ * local column k in the global list of ncols_total columns; every index must be owned by exactly one rank.  Returns
+ * the CSC of ALL ncols_total columns, resident on this rank's device and identical on every rank (read it with
+ * SLIMB200_ResultToHost / ResultToDevice / ResultToModel).  One grouped NCCL collective (variable-length all-gather)
+ * plus two placement kernels; nothing is padded and no shard passes through the host. */
+slimb200_result_t *SLIMB200_AllGatherColumns(slimb200_comm_t *comm, const slimb200_result_t *local,
+                                             const int32_t *positions, int32_t ncols_total, int32_t *r_status);
+/* Model handle (both views of SaveModel, estimate.c:570-593) from a result that holds ALL item columns 0..n-1 in
+ * order (SLIMB200_LearnColumns with cols == NULL, or SLIMB200_AllGatherColumns with positions = column ids); the
+ * CSR index (gk_csr_CreateIndex, lib/GKlib/csr.c:1546-1584) is built on the GPU. */
+slim_t *SLIMB200_ResultToModel(const slimb200_result_t *result, int32_t *r_status);
+
 /* Build a model handle (both views, reference SaveModel src/libslim/estimate.c:570-593) from the
  * CSC of all nitems columns, e.g. after gathering the shards of every GPU. */
 slim_t *SLIMB200_AssembleModel(int32_t nitems, const int64_t *colptr, const int32_t *colind,

@@ -60,6 +60,11 @@ _SIGNATURES = {
     "SLIMB200_ResultPhases": (C.c_int32, [C.c_void_p, c_f32p, c_i32p]),
     "SLIMB200_ResultToHost": (C.c_int32, [C.c_void_p, c_i64p, c_i32p, c_f32p]),
     "SLIMB200_ResultToDevice": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "SLIMB200_CommUniqueId": (C.c_int32, [C.c_void_p]),
+    "SLIMB200_CommInitRank": (C.c_void_p, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_i32p]),
+    "SLIMB200_CommFree": (None, [C.POINTER(C.c_void_p)]),
+    "SLIMB200_AllGatherColumns": (C.c_void_p, [C.c_void_p, C.c_void_p, c_i32p, C.c_int32, c_i32p]),
+    "SLIMB200_ResultToModel": (C.c_void_p, [C.c_void_p, c_i32p]),
     "SLIMB200_AssembleModel": (C.c_void_p, [C.c_int32, c_i64p, c_i32p, c_f32p, c_i32p]),
 }
 

@@ -15,11 +15,11 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libslim.so"
 SOURCES = [CSRC / "engine.cu", CSRC / "api.cpp"]
-HEADERS = [CSRC / "engine.h", CSRC / "gram.cuh", CSRC / "gram_batch.cuh", CSRC / "predict.cuh", PKG.parent / "include" / "slim.h", PKG.parent / "include" / "slim_b200.h"]
+HEADERS = [CSRC / "engine.h", CSRC / "gram.cuh", CSRC / "gram_batch.cuh", CSRC / "predict.cuh", CSRC / "gather.cuh", PKG.parent / "include" / "slim.h", PKG.parent / "include" / "slim_b200.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared", "-ldl",
 ]
 
 

@@ -11,7 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 // the library is built with -fvisibility=hidden: only the C ABI is exported
@@ -125,8 +129,10 @@ int env_device() {
   return (v && *v) ? atoi(v) : 0;
 }
 
+// `ordered` only changes the model-type label of the reference when nnbrs == 0 (api.c:54-60): the learner is the
+// same SLIM path, so it is accepted and ignored.
 bool supported(const Options &p, int32_t *status) {
-  if (p.algo != SLIM_ALGO_CD || p.nnbrs != 0 || p.ordered != 0) {
+  if (p.algo != SLIM_ALGO_CD || p.nnbrs != 0) {
     fprintf(stderr, "libslim (slim-b200): only algo=cd with nnbrs=0 is implemented on the GPU engine\n");
     if (status) *status = SLIM_ERROR_INPUT;
     return false;
@@ -156,6 +162,192 @@ CsrHandle *assemble(int32_t nitems, const int64_t *colptr, const int32_t *colind
   return h;
 }
 
+// SaveModel (estimate.c:570-593) from a device-resident Result that holds ALL item columns in order: the CSC is
+// copied as is, the CSR index (gk_csr_CreateIndex(ROW), csr.c:1546-1584) is built on the GPU (gather.cuh) and
+// lands directly in the malloc'd arrays of the handle.
+CsrHandle *model_from_result(const Result *res, int32_t *st) {
+  int32_t nitems = 0;
+  int64_t nnz = 0;
+  result_info(res, &nitems, &nnz, nullptr);
+  CsrHandle *h = handle_create();
+  if (h) {
+    h->nrows = h->ncols = nitems;  // SaveModel(tnnz, ncols, ncols, ...), estimate.c:544
+    h->colptr = xmalloc<ssize_t>((size_t)nitems + 1);
+    h->colind = xmalloc<int32_t>(nnz);
+    h->colval = xmalloc<float>(nnz);
+    h->rowptr = xmalloc<ssize_t>((size_t)nitems + 1);
+    h->rowind = xmalloc<int32_t>(nnz);
+    h->rowval = xmalloc<float>(nnz);
+  }
+  if (!h || !h->colptr || !h->colind || !h->colval || !h->rowptr || !h->rowind || !h->rowval) {
+    handle_free(h);
+    if (st) *st = SLIM_ERROR_MEMORY;
+    return nullptr;
+  }
+  const int rc = model_to_host(res, h->colptr, h->colind, h->colval, h->rowptr, h->rowind, h->rowval, nullptr);
+  if (rc != kOk) {
+    handle_free(h);
+    if (st) *st = rc;
+    return nullptr;
+  }
+  if (st) *st = SLIM_OK;
+  return h;
+}
+
+// ---- in-library multi-GPU -----------------------------------------------------------
+// Devices used by SLIM_Learn / Py_SLIM_Learn / Py_SLIM_Mselect.  SLIMB200_DEVICES="0,2,3" names them;
+// SLIMB200_GPUS=n takes n devices starting at SLIMB200_DEVICE (default 0).  Without either: every visible device
+// when the matrix is large enough for the replicated staging to pay (>= 20 M nonzeros), else one.
+std::vector<int> learn_devices(int64_t nnz) {
+  const int have = device_count();
+  std::vector<int> devs;
+  if (const char *list = getenv("SLIMB200_DEVICES")) {
+    for (const char *p = list; *p;) {
+      char *e;
+      const long d = strtol(p, &e, 10);
+      if (e == p) break;
+      if (d >= 0 && d < have && std::find(devs.begin(), devs.end(), (int)d) == devs.end()) devs.push_back((int)d);
+      p = (*e == ',') ? e + 1 : e;
+    }
+    if (!devs.empty()) return devs;
+  }
+  const int base = env_device();
+  int n = 1;
+  if (const char *g = getenv("SLIMB200_GPUS")) n = atoi(g);
+  else if (nnz >= 20000000) n = have;
+  n = std::max(1, std::min(n, std::max(have - base, 1)));
+  for (int k = 0; k < n; k++) devs.push_back(base + k);
+  return devs;
+}
+
+// one NCCL communicator per device, created once per device set and kept for the life of the process
+std::mutex g_comm_mutex;
+std::map<std::vector<int>, std::vector<Comm *>> g_comms;
+std::vector<Comm *> comms_for(const std::vector<int> &devs) {
+  std::lock_guard<std::mutex> lock(g_comm_mutex);
+  auto it = g_comms.find(devs);
+  if (it != g_comms.end()) return it->second;
+  std::vector<Comm *> cs(devs.size(), nullptr);
+  if (comm_init_all((int)devs.size(), devs.data(), cs.data()) != kOk) return {};
+  g_comms[devs] = cs;
+  return cs;
+}
+
+// columns of rank r: dealt round-robin in descending-nnz order (every rank gets the same head / tail mix)
+std::vector<int32_t> shard_of(const std::vector<int32_t> &order, int r, int W) {
+  std::vector<int32_t> cols;
+  for (size_t k = (size_t)r; k < order.size(); k += (size_t)W) cols.push_back(order[k]);
+  std::sort(cols.begin(), cols.end());
+  return cols;
+}
+
+struct MultiGpu {  // R replicated on every device of `devs`
+  std::vector<int> devs;
+  std::vector<Matrix *> mats;
+  std::vector<Comm *> comms;
+  std::vector<std::vector<int32_t>> shards;
+  int32_t ncols = 0;
+  std::string error;
+  int32_t status = SLIM_OK;
+  ~MultiGpu() {
+    for (Matrix *m : mats) free_matrix(m);
+  }
+};
+
+bool stage_multi(MultiGpu &g, int32_t nrows, const ssize_t *rowptr, const int32_t *rowind, const float *rowval) {
+  const size_t W = g.devs.size();
+  g.mats.assign(W, nullptr);
+  std::vector<int32_t> st(W, SLIM_OK);
+  std::vector<std::string> err(W);
+  std::vector<std::thread> th;
+  for (size_t r = 0; r < W; r++)
+    th.emplace_back([&, r] {
+      g.mats[r] = stage(g.devs[r], nrows, rowptr, rowind, rowval, false, 0, &st[r]);
+      if (!g.mats[r]) err[r] = last_error();
+    });
+  for (auto &t : th) t.join();
+  for (size_t r = 0; r < W; r++)
+    if (!g.mats[r]) {
+      g.error = err[r];
+      g.status = st[r];
+      return false;
+    }
+  matrix_info(g.mats[0], nullptr, &g.ncols, nullptr, nullptr, nullptr, nullptr);
+  std::vector<int32_t> cnt((size_t)std::max(g.ncols, 1));
+  matrix_colcounts(g.mats[0], cnt.data());
+  std::vector<int32_t> order(g.ncols);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cnt[a] > cnt[b]; });
+  g.shards.clear();
+  for (size_t r = 0; r < W; r++) g.shards.push_back(shard_of(order, (int)r, (int)W));
+  g.comms = comms_for(g.devs);
+  if (g.comms.empty()) {
+    g.error = last_error();
+    g.status = SLIM_ERROR;
+    return false;
+  }
+  return true;
+}
+
+// every device solves its shard, then ONE NCCL all-gather assembles W on every device; returns the gathered
+// Result of rank 0 (all columns, device resident) and sums the per-column residual / objective statistics
+Result *learn_multi(MultiGpu &g, const LearnParams &lp, const WarmStart *wsp, double *error, double *objval) {
+  const size_t W = g.devs.size();
+  std::vector<Result *> full(W, nullptr);
+  std::vector<int32_t> st(W, SLIM_OK);
+  std::vector<std::string> err(W);
+  std::vector<double> e_r(W, 0.0), o_r(W, 0.0);
+  // phase 1: the shards, side by side (no communication: the columns are independent problems)
+  std::vector<Result *> loc(W, nullptr);
+  {
+    std::vector<std::thread> th;
+    for (size_t r = 0; r < W; r++)
+      th.emplace_back([&, r] {
+        const std::vector<int32_t> &cols = g.shards[r];
+        loc[r] = learn(g.mats[r], lp, cols.data(), (int32_t)cols.size(), wsp, &st[r]);
+        if (!loc[r]) {
+          err[r] = last_error();
+          return;
+        }
+        std::vector<double> rn(cols.size()), ob(cols.size());
+        result_stats(loc[r], nullptr, nullptr, nullptr, nullptr, rn.data(), ob.data());
+        for (size_t k = 0; k < cols.size(); k++) {
+          e_r[r] += rn[k];
+          o_r[r] += ob[k];
+        }
+      });
+    for (auto &t : th) t.join();
+  }
+  bool solved = true;
+  for (size_t r = 0; r < W; r++) solved = solved && loc[r] != nullptr;
+  // phase 2: the all-gather (every rank must take part, so it only starts when every shard was solved)
+  if (solved) {
+    std::vector<std::thread> th;
+    for (size_t r = 0; r < W; r++)
+      th.emplace_back([&, r] {
+        full[r] = allgather_columns(g.comms[r], loc[r], g.shards[r].data(), g.ncols, &st[r]);
+        if (!full[r]) err[r] = last_error();
+      });
+    for (auto &t : th) t.join();
+  }
+  for (size_t r = 0; r < W; r++) free_result(loc[r]);
+  bool ok = true;
+  for (size_t r = 0; r < W; r++)
+    if (!full[r]) {
+      ok = false;
+      g.error = err[r];
+      g.status = st[r];
+    }
+  for (size_t r = 1; r < W; r++) free_result(full[r]);
+  if (!ok) {
+    free_result(full[0]);
+    return nullptr;
+  }
+  if (error) *error = std::accumulate(e_r.begin(), e_r.end(), 0.0);
+  if (objval) *objval = std::accumulate(o_r.begin(), o_r.end(), 0.0);
+  return full[0];
+}
+
 // Body shared by SLIM_Learn (api.c:33-96) and Py_SLIM_Learn (pyapi.c:134-199).
 CsrHandle *learn_entry(int32_t nrows, const ssize_t *rowptr, const int32_t *rowind, const float *rowval,
                        const int32_t *io, const double *dopt, const CsrHandle *imodel, int32_t *r_status) {
@@ -163,17 +355,11 @@ CsrHandle *learn_entry(int32_t nrows, const ssize_t *rowptr, const int32_t *rowi
   int32_t st = SLIM_OK;
   if (r_status) *r_status = SLIM_ERROR;
   if (!supported(p, r_status)) return nullptr;
-  if (p.dbglvl & SLIM_DBG_INFO) print_params(p);
-
-  const double t0 = now_s();
-  Matrix *m = stage(env_device(), nrows, rowptr, rowind, rowval, false, 0, &st);
-  const double t1 = now_s();
-  if (!m) {
-    fprintf(stderr, "libslim (slim-b200): staging failed: %s\n", last_error());
-    if (r_status) *r_status = st;
+  if (nrows < 0 || !rowptr) {
+    if (r_status) *r_status = SLIM_ERROR_INPUT;
     return nullptr;
   }
-  printf("Using Coordinate Descent! \n");  // estimate.c:329
+  if (p.dbglvl & SLIM_DBG_INFO) print_params(p);
 
   LearnParams lp{p.l1r, p.l2r, p.opttol, p.maxniters, p.dbglvl};
   WarmStart ws{};
@@ -185,34 +371,61 @@ CsrHandle *learn_entry(int32_t nrows, const ssize_t *rowptr, const int32_t *rowi
     ws.colval = imodel->colval;
     wsp = &ws;
   }
-  Result *res = learn(m, lp, nullptr, 0, wsp, &st);
+
+  const double t0 = now_s();
+  const std::vector<int> devs = learn_devices((int64_t)rowptr[nrows]);
   CsrHandle *model = nullptr;
-  if (res) {
-    int32_t nsel = 0;
-    int64_t nnz = 0;
-    result_info(res, &nsel, &nnz, nullptr);
-    std::vector<int64_t> cp((size_t)nsel + 1);
-    std::vector<int32_t> ci((size_t)std::max<int64_t>(nnz, 1));
-    std::vector<float> cv((size_t)std::max<int64_t>(nnz, 1));
-    st = result_to_host(res, cp.data(), ci.data(), cv.data());
-    if (st == kOk) {
-      model = assemble(nsel, cp.data(), ci.data(), cv.data());
-      if (!model) st = SLIM_ERROR_MEMORY;
+  double t1 = t0, error = 0.0, objval = 0.0;
+  Result *res = nullptr;  // all columns, device resident
+  MultiGpu mg;
+  Matrix *m = nullptr;
+  const char *force_multi = getenv("SLIMB200_FORCE_MULTI");  // tests: the sharded path on a single device
+  if (devs.size() > 1 || (force_multi && atoi(force_multi))) {
+    // column-sharded over the devices of this process: R replicated, one NCCL all-gather of W at the end
+    mg.devs = devs;
+    const bool staged = stage_multi(mg, nrows, rowptr, rowind, rowval);
+    t1 = now_s();
+    if (!staged) {
+      fprintf(stderr, "libslim (slim-b200): multi-GPU staging failed: %s\n", mg.error.c_str());
+      if (r_status) *r_status = mg.status;
+      return nullptr;
     }
-    if (model && (p.dbglvl & SLIM_DBG_INFO)) {  // estimate.c:552-555
+    printf("Using Coordinate Descent! \n");  // estimate.c:329
+    res = learn_multi(mg, lp, wsp, &error, &objval);
+    if (!res) {
+      st = mg.status;
+      fprintf(stderr, "libslim (slim-b200): multi-GPU learn failed: %s\n", mg.error.c_str());
+    }
+  } else {
+    m = stage(devs.empty() ? env_device() : devs[0], nrows, rowptr, rowind, rowval, false, 0, &st);
+    t1 = now_s();
+    if (!m) {
+      fprintf(stderr, "libslim (slim-b200): staging failed: %s\n", last_error());
+      if (r_status) *r_status = st;
+      return nullptr;
+    }
+    printf("Using Coordinate Descent! \n");  // estimate.c:329
+    res = learn(m, lp, nullptr, 0, wsp, &st);
+    if (res) {
+      int32_t nsel = 0;
+      result_info(res, &nsel, nullptr, nullptr);
       std::vector<double> rn(nsel), ob(nsel);
       result_stats(res, nullptr, nullptr, nullptr, nullptr, rn.data(), ob.data());
-      double error = 0.0, objval = 0.0;
       for (int32_t j = 0; j < nsel; j++) {
         error += rn[j];
         objval += ob[j];
       }
-      printf("Done estimation: loss: %.5le, fit: %.5le, ffrac: %.3lf,  #nzs: %zd\n", objval, error,
-             error / objval, (ssize_t)nnz);
+    } else {
+      fprintf(stderr, "libslim (slim-b200): learn failed: %s\n", last_error());
     }
+  }
+  if (res) {
+    model = model_from_result(res, &st);
+    if (!model) fprintf(stderr, "libslim (slim-b200): model assembly failed: %s\n", last_error());
+    if (model && (p.dbglvl & SLIM_DBG_INFO))  // estimate.c:552-555
+      printf("Done estimation: loss: %.5le, fit: %.5le, ffrac: %.3lf,  #nzs: %zd\n", objval, error, error / objval,
+             model->colptr[model->ncols]);
     free_result(res);
-  } else {
-    fprintf(stderr, "libslim (slim-b200): learn failed: %s\n", last_error());
   }
   const double t2 = now_s();
   free_matrix(m);
@@ -330,12 +543,14 @@ CsrHandle *wrap_csr(int32_t nrows, const ssize_t *rowptr, const int32_t *rowind,
   h->ncols = max_index_plus1(nnz, rowind);
   h->rowptr = xmalloc<ssize_t>((size_t)nrows + 1);
   h->rowind = xmalloc<int32_t>(nnz);
+  if (rowval) h->rowval = xmalloc<float>(nnz);
+  if (!h->rowptr || !h->rowind || (rowval && !h->rowval)) {
+    handle_free(h);
+    return nullptr;
+  }
   memcpy(h->rowptr, rowptr, sizeof(ssize_t) * ((size_t)nrows + 1));
   memcpy(h->rowind, rowind, sizeof(int32_t) * nnz);
-  if (rowval) {
-    h->rowval = xmalloc<float>(nnz);
-    memcpy(h->rowval, rowval, sizeof(float) * nnz);
-  }
+  if (rowval) memcpy(h->rowval, rowval, sizeof(float) * nnz);
   return h;
 }
 
@@ -390,23 +605,33 @@ slim_t *SLIM_ReadModel(char *filename) {
   FILE *f = fopen(filename, "rb");
   if (!f) return nullptr;
   CsrHandle *h = handle_create();
-  bool ok = h && fread(&h->nrows, sizeof(int32_t), 1, f) == 1 && fread(&h->ncols, sizeof(int32_t), 1, f) == 1 &&
+  if (!h) {
+    fclose(f);
+    return nullptr;
+  }
+  bool ok = fread(&h->nrows, sizeof(int32_t), 1, f) == 1 && fread(&h->ncols, sizeof(int32_t), 1, f) == 1 &&
             h->nrows >= 0 && h->ncols >= 0;
   if (ok) {
     h->rowptr = xmalloc<ssize_t>((size_t)h->nrows + 1);
-    ok = fread(h->rowptr, sizeof(ssize_t), (size_t)h->nrows + 1, f) == (size_t)h->nrows + 1;
+    ok = h->rowptr && fread(h->rowptr, sizeof(ssize_t), (size_t)h->nrows + 1, f) == (size_t)h->nrows + 1;
+  }
+  if (ok) {  // the row pointer must be a monotone prefix sum starting at 0
+    ok = h->rowptr[0] == 0;
+    for (int32_t i = 0; ok && i < h->nrows; i++) ok = h->rowptr[i + 1] >= h->rowptr[i];
   }
   if (ok) {
     const ssize_t nnz = h->rowptr[h->nrows];
     h->rowind = xmalloc<int32_t>(nnz);
     h->rowval = xmalloc<float>(nnz);
-    ok = fread(h->rowind, sizeof(int32_t), nnz, f) == (size_t)nnz &&
+    ok = h->rowind && h->rowval && fread(h->rowind, sizeof(int32_t), nnz, f) == (size_t)nnz &&
          fread(h->rowval, sizeof(float), nnz, f) == (size_t)nnz;
+    for (ssize_t k = 0; ok && k < nnz; k++) ok = h->rowind[k] >= 0 && h->rowind[k] < h->ncols;
     if (ok) {
       h->colptr = xmalloc<ssize_t>((size_t)h->ncols + 1);
       h->colind = xmalloc<int32_t>(nnz);
       h->colval = xmalloc<float>(nnz);
-      transpose(h->nrows, h->ncols, h->rowptr, h->rowind, h->rowval, h->colptr, h->colind, h->colval);
+      ok = h->colptr && h->colind && h->colval;
+      if (ok) transpose(h->nrows, h->ncols, h->rowptr, h->rowind, h->rowval, h->colptr, h->colind, h->colval);
     }
   }
   fclose(f);
@@ -554,14 +779,16 @@ int32_t Py_SLIM_Predict(int32_t nrcmds, slim_t *slimhandle, slim_t *trnhandle, i
   const CsrHandle *w = static_cast<const CsrHandle *>(slimhandle);
   const CsrHandle *t = static_cast<const CsrHandle *>(trnhandle);
   if (!w || !t || !w->rowptr || !t->rowptr) return SLIM_ERROR;
-  // batched on the GPU (predict.cuh): one CTA per user, lists and scores bit-identical to recommend() below.
-  // SLIMB200_PREDICT_HOST=1 (or no usable device) keeps the per-user host loop of the reference.
+  // batched on the GPU (predict.cuh): one CTA per user, lists and scores bit-identical to recommend() below; a
+  // failing GPU call is an error.  The per-user host loop of the reference (pyapi.c:530-563) runs only when it is
+  // asked for (SLIMB200_PREDICT_HOST=1) or when the process has no CUDA device at all (prediction is not the
+  // learner: a model can be served on a host without a GPU, exactly as with the reference library).
   const char *force_host = getenv("SLIMB200_PREDICT_HOST");
   if (nrcmds > 0 && t->nrows > 0 && device_count() > 0 && !(force_host && atoi(force_host))) {
     const int rc = predict_topn(env_device(), w->nrows, w->ncols, w->rowptr, w->rowind, w->rowval, t->nrows, t->rowptr,
                                 t->rowind, t->rowval, nrcmds, output, scores, nullptr, nullptr);
-    if (rc == kOk) return SLIM_OK;
-    fprintf(stderr, "[slim-b200] GPU top-N failed (%s): using the host loop\n", last_error());
+    if (rc != kOk) fprintf(stderr, "libslim (slim-b200): GPU top-N failed: %s\n", last_error());
+    return rc == kOk ? SLIM_OK : SLIM_ERROR;  // no silent host fallback once a device was chosen
   }
   std::vector<int32_t> rids((size_t)std::max(nrcmds, 1));
   std::vector<float> rsc((size_t)std::max(nrcmds, 1));
@@ -627,14 +854,7 @@ int32_t Py_SLIM_Mselect(slim_t *trnhandle, slim_t *tsthandle, int32_t *ioptions,
       Result *res = learn(m, lp, nullptr, 0, model ? &ws : nullptr, &st);
       CsrHandle *next = nullptr;
       if (res) {
-        int32_t nsel = 0;
-        int64_t nnz = 0;
-        result_info(res, &nsel, &nnz, nullptr);
-        std::vector<int64_t> cp((size_t)nsel + 1);
-        std::vector<int32_t> ci((size_t)std::max<int64_t>(nnz, 1));
-        std::vector<float> cv((size_t)std::max<int64_t>(nnz, 1));
-        if (result_to_host(res, cp.data(), ci.data(), cv.data()) == kOk)
-          next = assemble(nsel, cp.data(), ci.data(), cv.data());
+        next = model_from_result(res, &st);
         free_result(res);
       }
       handle_free(model);
@@ -647,19 +867,27 @@ int32_t Py_SLIM_Mselect(slim_t *trnhandle, slim_t *tsthandle, int32_t *ioptions,
       }
       // evaluation, pyapi.c:306-366
       std::fill(rmarker.begin(), rmarker.end(), -1);
-      double hr[3] = {0, 0, 0}, arhr = 0.0;
+      float hr[3] = {0, 0, 0}, arhr = 0.0f;  // float accumulators, as pyapi.c:231 declares them
       int32_t nvalid = 0, nvalid_head = 0, nvalid_tail = 0;
-      // top-N lists of all users in one batched GPU call (predict.cuh); per-user host loop as the fallback
+      // top-N lists of all users in one batched GPU call (predict.cuh); SLIMB200_PREDICT_HOST=1 asks for the
+      // per-user loop of the reference instead.  A failing GPU call ends the grid with an error (no silent fallback).
       bool gpu_lists = false;
       {
         const char *force_host = getenv("SLIMB200_PREDICT_HOST");
-        if (p.nrcmds > 0 && trn->nrows > 0 && device_count() > 0 && !(force_host && atoi(force_host))) {
+        if (p.nrcmds > 0 && trn->nrows > 0 && !(force_host && atoi(force_host))) {
           all_ids.assign((size_t)trn->nrows * p.nrcmds, -1);
           all_sc.assign((size_t)trn->nrows * p.nrcmds, 0.f);
           all_cnt.assign((size_t)trn->nrows, 0);
           gpu_lists = predict_topn(env_device(), model->nrows, model->ncols, model->rowptr, model->rowind,
                                    model->rowval, trn->nrows, trn->rowptr, trn->rowind, trn->rowval, p.nrcmds,
                                    all_ids.data(), all_sc.data(), all_cnt.data(), nullptr) == kOk;
+          if (!gpu_lists) {
+            fprintf(stderr, "libslim (slim-b200): GPU top-N failed: %s\n", last_error());
+            *bestl1HR = arrayl1[i1];
+            *bestl2HR = arrayl2[i2];
+            rc = SLIM_ERROR;
+            break;
+          }
         }
       }
       for (int32_t u = 0; u < trn->nrows; u++) {
@@ -676,7 +904,7 @@ int32_t Py_SLIM_Mselect(slim_t *trnhandle, slim_t *tsthandle, int32_t *ioptions,
         }
         nvalid += n >= 0 ? 1 : 0;
         int is_tail = 0, is_head = 0, ntrue[2] = {0, 0}, nhits[3] = {0, 0, 0};
-        double larhr = 0.0, baseline = 0.0;
+        float larhr = 0.0f, baseline = 0.0f;
         for (ssize_t z = tst->rowptr[u]; z < tst->rowptr[u + 1]; z++) {
           rmarker[tst->rowind[z]] = u;
           ntrue[fm[tst->rowind[z]]]++;
@@ -842,6 +1070,34 @@ int32_t SLIMB200_ResultToDevice(const slimb200_result_t *result, int32_t *d_coun
                                 float *d_colval) {
   if (!result) return SLIM_ERROR_INPUT;
   return result_to_device(reinterpret_cast<const Result *>(result), d_counts, d_colind, d_colval);
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------
+int32_t SLIMB200_CommUniqueId(void *id128) { return id128 ? comm_unique_id(id128) : SLIM_ERROR_INPUT; }
+
+slimb200_comm_t *SLIMB200_CommInitRank(int32_t device, int32_t nranks, int32_t rank, const void *id128,
+                                       int32_t *r_status) {
+  return reinterpret_cast<slimb200_comm_t *>(comm_init(device, nranks, rank, id128, r_status));
+}
+
+void SLIMB200_CommFree(slimb200_comm_t **comm) {
+  if (!comm) return;
+  comm_free(reinterpret_cast<Comm *>(*comm));
+  *comm = nullptr;
+}
+
+slimb200_result_t *SLIMB200_AllGatherColumns(slimb200_comm_t *comm, const slimb200_result_t *local,
+                                             const int32_t *positions, int32_t ncols_total, int32_t *r_status) {
+  if (r_status) *r_status = SLIM_ERROR_INPUT;
+  if (!comm || !local) return nullptr;
+  return reinterpret_cast<slimb200_result_t *>(allgather_columns(
+      reinterpret_cast<Comm *>(comm), reinterpret_cast<const Result *>(local), positions, ncols_total, r_status));
+}
+
+slim_t *SLIMB200_ResultToModel(const slimb200_result_t *result, int32_t *r_status) {
+  if (r_status) *r_status = SLIM_ERROR_INPUT;
+  if (!result) return nullptr;
+  return model_from_result(reinterpret_cast<const Result *>(result), r_status);
 }
 
 slim_t *SLIMB200_AssembleModel(int32_t nitems, const int64_t *colptr, const int32_t *colind, const float *colval,

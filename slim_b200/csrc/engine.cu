@@ -32,7 +32,10 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_sort.cuh>
 
 namespace cg = cooperative_groups;
@@ -183,6 +186,8 @@ struct Matrix {
 
 void free_matrix(Matrix *m) {
   if (!m) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(m->device);
   cudaFree(m->d_rowptr);
   cudaFree(m->d_rowind);
@@ -205,6 +210,7 @@ void free_matrix(Matrix *m) {
   if (m->stream3) cudaStreamDestroy(m->stream3);
   if (m->stream4) cudaStreamDestroy(m->stream4);
   if (m->stream) cudaStreamDestroy(m->stream);
+  if (prev >= 0 && prev != m->device) cudaSetDevice(prev);  // leave the caller's current device as it was
   delete m;
 }
 
@@ -516,9 +522,8 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
       throw EngineError(kErrInput, "stage: nnz must be in [0, 2^32)");
     if (!rowind && nnz > 0) throw EngineError(kErrInput, "stage: rowind is NULL");
 
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    EventPair stage_ev;  // destroyed on every exit path
+    cudaEvent_t e0 = stage_ev.a, e1 = stage_ev.b;
     CK(cudaEventRecord(e0, s));
 
     CK(cudaMalloc(&m->d_rowptr, sizeof(int64_t) * ((size_t)nrows + 1)));
@@ -721,8 +726,6 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     m->stage_ms = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (status) *status = kOk;
     return m;
   } catch (const EngineError &e) {
@@ -734,6 +737,11 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
   }
   free_matrix(m);
   return nullptr;
+}
+
+int matrix_colcounts(const Matrix *m, int32_t *cnt) {
+  for (int32_t c = 0; c < m->ncols; c++) cnt[c] = m->h_colcnt[m->h_rank[c]];
+  return kOk;
 }
 
 int matrix_item_order_to_host(const Matrix *m, int32_t *rank) {
@@ -2673,6 +2681,8 @@ int result_to_device(const Result *r, int32_t *d_counts, int32_t *d_colind, floa
     return e.status;
   }
 }
+
+#include "gather.cuh"
 
 struct LaunchPlan {
   int nt;

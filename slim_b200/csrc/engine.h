@@ -81,6 +81,24 @@ int predict_topn(int device, int32_t wrows, int32_t wcols, const ssize_t *wrowpt
                  const float *urowval, int32_t nrcmds, int32_t *out_ids, float *out_scores, int32_t *out_counts,
                  double *kernel_ms);
 
+// Column nnz by ORIGINAL item id (host copy kept by stage()).
+int matrix_colcounts(const Matrix *m, int32_t *cnt);
+
+// ---- multi-GPU (gather.cuh): NCCL communicators and the final all-gather of W ------------------
+struct Comm;
+int comm_unique_id(void *id128);  // 128 bytes (ncclUniqueId), to be broadcast to the other ranks by the caller
+Comm *comm_init(int device, int nranks, int rank, const void *id128, int32_t *status);
+int comm_init_all(int ndev, const int *devices, Comm **out);  // one communicator per device, all in this process
+void comm_free(Comm *c);
+void comm_info(const Comm *c, int32_t *nranks, int32_t *rank, int32_t *device);
+// All-gather of the column shards: positions[k] = index of local column k in the global list of ncols_total columns.
+// Returns the CSC of all ncols_total columns on the communicator's device (same content on every rank).
+Result *allgather_columns(Comm *c, const Result *local, const int32_t *positions, int32_t ncols_total, int32_t *status);
+// Both views of a model (SaveModel, estimate.c:570-593) from a Result holding ALL columns 0..n-1 in order; the CSR
+// index is built on the GPU.  Arrays are caller-allocated ([n+1] / [nnz]); index_ms = CUDA-event time of the index build.
+int model_to_host(const Result *r, ssize_t *colptr, int32_t *colind, float *colval, ssize_t *rowptr, int32_t *rowind,
+                  float *rowval, double *index_ms);
+
 int device_count();
 const char *last_error();
 

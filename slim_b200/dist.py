@@ -1,10 +1,18 @@
-"""Column-sharded multi-GPU learning: one process per GPU (torch.distributed), R replicated, the
-target item columns dealt across ranks, and ONE exchange at the end that assembles W on every rank.
+"""Column-sharded multi-GPU learning with one process per GPU: R replicated, the target item columns
+dealt across ranks, and ONE exchange at the end that assembles W on every rank.
 
 The reference's only parallelism is `#pragma omp for schedule(dynamic,32)` over target columns
 (src/libslim/estimate.c:402-403) -- the columns are independent problems, so there is no data-path
-collective during the solve; the all-gather below is the NCCL (or gloo, in CPU tests) counterpart
-of SaveModel's concatenation of per-column lists (estimate.c:570-588).
+collective during the solve; the final all-gather is the counterpart of SaveModel's concatenation of
+per-column lists (estimate.c:570-588).
+
+The exchange itself lives in the LIBRARY (slim_b200/csrc/gather.cuh behind SLIMB200_AllGatherColumns):
+NCCL over NVLink, variable-length, reassembled on the device.  `Communicator` only carries the 128-byte
+NCCL id from rank 0 to the other ranks through torch.distributed (plumbing).  `all_gather_columns` below
+is the torch.distributed restatement of the same exchange: it runs with gloo on CPU tensors, which is how
+the host-side logic (sharding, reassembly order) is tested without GPUs, and it is what the multi-rank GPU
+test compares the library path with.  (Inside ONE process SLIM_Learn shards over the visible GPUs by
+itself; see include/slim_b200.h.)
 """
 from __future__ import annotations
 
@@ -84,24 +92,77 @@ def all_gather_columns(local_idx: np.ndarray, counts: torch.Tensor, colind: torc
     return colptr, out_ind, out_val
 
 
-def sharded_learn(staged, params, cols: np.ndarray | None = None, colcnt: np.ndarray | None = None,
-                  group=None, gather: bool = True):
-    """Solve `cols` (None: all columns) across the ranks of `group`; every rank holds a replica of R
-    (`staged`).  Returns (local ColumnResult, (colptr, colind, colval) of ALL columns or None)."""
+class Communicator:
+    """NCCL communicator owned by libslim.so (SLIMB200_CommInitRank), one per rank / GPU.  The 128-byte id
+    created on rank 0 travels to the other ranks through torch.distributed (any backend)."""
+
+    def __init__(self, device: int, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self._lib = _lib.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            rc = self._lib.SLIMB200_CommUniqueId(uid.ctypes.data_as(C.c_void_p))
+            if rc != 1:
+                raise RuntimeError("SLIMB200_CommUniqueId failed: " + (self._lib.SLIMB200_LastError() or b"").decode())
+        backend = dist.get_backend(group)
+        t = torch.from_numpy(uid)
+        if backend == "nccl":
+            t = t.to(torch.device("cuda", device))
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = t.cpu().numpy()
+        st = C.c_int32(0)
+        self.handle = self._lib.SLIMB200_CommInitRank(device, self.world, self.rank, uid.ctypes.data_as(C.c_void_p),
+                                                      C.byref(st))
+        if not self.handle:
+            raise RuntimeError("SLIMB200_CommInitRank failed (%d): %s" %
+                               (st.value, (self._lib.SLIMB200_LastError() or b"").decode()))
+
+    def all_gather_columns(self, local, positions: np.ndarray, ncols_total: int):
+        """Collective: `local` (ColumnResult) holds this rank's columns, positions[k] = index of local column k
+        in the global list.  Returns a ColumnResult with ALL columns, resident on this rank's GPU."""
+        import ctypes as C
+
+        from .core import ColumnResult
+
+        pos = np.ascontiguousarray(positions, dtype=np.int32)
+        st = C.c_int32(0)
+        h = self._lib.SLIMB200_AllGatherColumns(self.handle, local.handle, pos.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                int(ncols_total), C.byref(st))
+        if not h:
+            raise RuntimeError("SLIMB200_AllGatherColumns failed (%d): %s" %
+                               (st.value, (self._lib.SLIMB200_LastError() or b"").decode()))
+        return ColumnResult(self._lib, h)
+
+    def close(self):
+        import ctypes as C
+
+        if getattr(self, "handle", None):
+            h = C.c_void_p(self.handle)
+            self._lib.SLIMB200_CommFree(C.byref(h))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sharded_learn(staged, params, comm: Communicator, cols: np.ndarray | None = None,
+                  colcnt: np.ndarray | None = None, gather: bool = True):
+    """Solve `cols` (None: all columns) across the ranks of `comm`; every rank holds a replica of R
+    (`staged`).  Returns (local ColumnResult, ColumnResult with ALL columns on the device or None)."""
     from .core import learn_columns
 
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
     if cols is None:
         cols = np.arange(staged.ncols, dtype=np.int32)
     cols = np.ascontiguousarray(cols, dtype=np.int32)
-    mine = shard_columns(cols, colcnt, rank, world)
+    mine = shard_columns(cols, colcnt, comm.rank, comm.world)
     res = learn_columns(staged, params, cols=cols[mine])
     if not gather:
         return res, None
-    dev = torch.device("cuda", staged.device)
-    counts = torch.empty(max(res.nsel, 1), dtype=torch.int32, device=dev)
-    ind = torch.empty(max(res.nnz, 1), dtype=torch.int32, device=dev)
-    val = torch.empty(max(res.nnz, 1), dtype=torch.float32, device=dev)
-    res.to_device(counts, ind, val)
-    full = all_gather_columns(mine, counts[:res.nsel], ind[:res.nnz], val[:res.nnz], len(cols), group)
-    return res, full
+    return res, comm.all_gather_columns(res, mine, len(cols))
