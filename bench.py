@@ -375,6 +375,7 @@ def main():
         except Exception:
             traffic = None
     gram_eb, gram_ms = staged.gram_info()
+    gram_bytes, gram_h32, gram_h16 = staged.gram_layout()
     kernel_name = ("cd_gram_kernel + cd_gram_batch_kernel (Gram-space CD, concurrent launches)" if gram_eb
                    else "cd_cluster_kernel (user-space CD)")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -464,12 +465,14 @@ def main():
                             "parallelism": f"column-sharded x{world}, R replicated" +
                                            (f", one NCCL all-gather of W per step inside libslim.so ({allgather_ms:.1f} ms)"
                                             if world > 1 else ""),
-                            "l2_policy": ("inputs >> 126 MB L2 (the solver streams the 40 GB Gram matrix, ~54 TB of DRAM traffic per "
-                                          "step); different columns every step" if gram_eb else
+                            "l2_policy": ("inputs >> 126 MB L2 (the solver streams the %.0f GB Gram matrix, tens of TB of DRAM traffic "
+                                          "per step); different columns every step" % (gram_bytes / 1e9) if gram_eb else
                                           "inputs (2 GB CSR+CSC) >> 126 MB L2; different columns every step"),
                             "datagen_s": round(gen_s, 2), "stage_ms": round(staged.stage_ms, 2),
-                            "gram": {"elem_bytes": gram_eb, "build_ms": round(gram_ms, 1),
-                                     "GB": round(gram_eb * staged.ncols * staged.ncols / 1e9, 2)}},
+                            "gram": {"layout": ("packed unsigned: 32-bit columns [0,%d), 16-bit [%d,%d), 8-bit beyond"
+                                                % (gram_h32, gram_h32, gram_h16)) if gram_eb == 4 else
+                                               ("fp64" if gram_eb == 8 else "not staged"),
+                                     "build_ms": round(gram_ms, 1), "GB": round(gram_bytes / 1e9, 2)}},
                     roofline=roofline, cpu_baseline=cpu_baseline, parity_check=parity_check, e2e=e2e, clocks=clocks,
                     gpu_launches=int(launches))
         print(json.dumps(line))

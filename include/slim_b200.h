@@ -51,11 +51,16 @@ int32_t SLIMB200_MatrixWindowGram(const slimb200_matrix_t *matrix, double *out);
 
 /* Gram matrix G = R^T R (internal item order) that staging builds for the Gram-space solver when it fits in
  * HBM: every <a_i, a_k> the coordinate-descent sweeps of cd.c:117-133 need.  elem_bytes = 0 (not staged:
- * too large, or SLIMB200_GRAM=0), 4 (float, exact: integer ratings and sums below 2^24) or 8 (double);
- * build_ms = CUDA-event time of the build.  SLIMB200_MatrixGram copies it back densely, ncols x ncols
- * elements of that type without row padding (tests). */
+ * too large, or SLIMB200_GRAM=0), 4 (exact integer sums: non-negative integer ratings and sums below 2^24; stored
+ * PACKED, 32 / 16 / 8 bits per element depending on the column's bound, see SLIMB200_MatrixGramLayout) or 8 (double);
+ * build_ms = CUDA-event time of the build.  SLIMB200_MatrixGram copies it back densely, ncols x ncols elements
+ * without row padding -- float for elem_bytes 4, double for 8 (tests). */
 int32_t SLIMB200_MatrixGramInfo(const slimb200_matrix_t *matrix, int32_t *elem_bytes, double *build_ms);
 int32_t SLIMB200_MatrixGram(const slimb200_matrix_t *matrix, void *out);
+/* Footprint in HBM and column ranges of the packed layout: columns (internal ids) [0, h32) hold 32-bit elements,
+ * [h32, h16) 16-bit, the rest 8-bit; a column's width follows from the bound G[k][i] <= rmax * sum_u r_ui^2.
+ * h32 = h16 = 0 for the fp64 layout.  Any pointer may be NULL. */
+int32_t SLIMB200_MatrixGramLayout(const slimb200_matrix_t *matrix, int64_t *bytes, int32_t *h32, int32_t *h16);
 
 /* Solve target columns cols[0..ncols_sel) (cols == NULL: every column): the per-column body of
  * EstimateModelCD (reference src/libslim/estimate.c:405-505) + CoordinateDescent (cd.c:101-142).

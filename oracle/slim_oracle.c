@@ -42,6 +42,13 @@ oracle_csc_t *oracle_setup(int32_t nrows, const int64_t *rowptr, const int32_t *
   m->colval = rowval ? (float *)malloc(sizeof(float) * (size_t)(nnz > 0 ? nnz : 1)) : NULL;
   m->cnorms = (float *)calloc((size_t)(ncols > 0 ? ncols : 1), sizeof(float));
 
+  m->rowptr = (int64_t *)malloc(sizeof(int64_t) * ((size_t)nrows + 1));
+  m->rowind = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
+  m->rowval = rowval ? (float *)malloc(sizeof(float) * (size_t)(nnz > 0 ? nnz : 1)) : NULL;
+  memcpy(m->rowptr, rowptr, sizeof(int64_t) * ((size_t)nrows + 1));
+  memcpy(m->rowind, rowind, sizeof(int32_t) * (size_t)nnz);
+  if (rowval) memcpy(m->rowval, rowval, sizeof(float) * (size_t)nnz);
+
   for (k = 0; k < nnz; k++) m->colptr[rowind[k] + 1]++;
   for (i = 0; i < ncols; i++) m->colptr[i + 1] += m->colptr[i];
   {
@@ -77,6 +84,9 @@ void oracle_free_csc(oracle_csc_t *m) {
   free(m->colind);
   free(m->colval);
   free(m->cnorms);
+  free(m->rowptr);
+  free(m->rowind);
+  free(m->rowval);
   free(m);
 }
 
@@ -140,9 +150,114 @@ static void shuffle_ref(act_t *list, int32_t n) {
 typedef struct {
   double *x, *aty, *y, *yhat, *csq;
   act_t *act;
-  const int32_t *rank; /* ORACLE_ORDER_POPULARITY: position of every item in the visiting order */
+  const int32_t *rank; /* position of every item when sorted by (descending nnz, ascending id) */
   act_t *tmp;
+  int32_t *marker; /* fSLIM: candidate slot of an item, -1 when it is none (neighbors.c:36-37) */
+  act_t *cand;
 } work_t;
+
+/* ------------------------------------------------------------------------------------------
+ * fSLIM neighbour search, restating src/libslim/neighbors.c:16-125 (FindColumnNeighbors).
+ * Candidates are the items that share a user with column jc, collected in first-encounter order
+ * (users of jc ascending, items of a user's row in row order); the similarity accumulates in
+ * FLOAT (gk_fkv_t.key), cosine divides by the CANDIDATE's norm only (neighbors.c:82-83) and
+ * "jaccard" uses norms, not squared norms (neighbors.c:108-110) -- both kept as they are.
+ * Returns min(nnbrs, ncand); the winners are cand[0 .. ret).
+ * ---------------------------------------------------------------------------------------- */
+static int pop_before(const work_t *w, const act_t *a, const act_t *b) {
+  if (a->key != b->key) return a->key > b->key;
+  return w->rank[a->val] < w->rank[b->val];
+}
+
+static int32_t find_neighbors(const oracle_csc_t *m, const oracle_params_t *p, int32_t jc, work_t *w) {
+  int64_t kk, j;
+  int32_t n = 0, i, want;
+  act_t *c = w->cand;
+  if (m->colptr[jc] == m->colptr[jc + 1]) return 0; /* neighbors.c:33-34 */
+  for (kk = m->colptr[jc]; kk < m->colptr[jc + 1]; kk++) {
+    const int32_t u = m->colind[kk];
+    const float cval = m->colval ? m->colval[kk] : 1.0f;
+    for (j = m->rowptr[u]; j < m->rowptr[u + 1]; j++) {
+      const int32_t it = m->rowind[j];
+      if (it == jc) continue;
+      if (w->marker[it] == -1) {
+        c[n].val = it;
+        c[n].key = 0.0f;
+        w->marker[it] = n++;
+      }
+      if (m->rowval) {
+        volatile float prod = m->rowval[j] * cval; /* separate multiply and add, as the -std=c99 build */
+        c[w->marker[it]].key = c[w->marker[it]].key + prod;
+      } else {
+        c[w->marker[it]].key = c[w->marker[it]].key + cval;
+      }
+    }
+  }
+  if (p->simtype == ORACLE_SIM_COS) {
+    for (i = 0; i < n; i++) c[i].key = c[i].key / m->cnorms[c[i].val];
+  } else if (p->simtype == ORACLE_SIM_JAC) {
+    for (i = 0; i < n; i++) c[i].key = c[i].key / (m->cnorms[c[i].val] + m->cnorms[jc] - c[i].key);
+  }
+  for (i = 0; i < n; i++) w->marker[c[i].val] = -1;
+  want = p->nnbrs < n ? p->nnbrs : n;
+  if (n <= want) return n;
+
+  if (p->nbr_ties == ORACLE_TIES_POPULARITY) {
+    /* deterministic rule: full order by (similarity desc, popularity rank asc); selection by repeated minimum
+       removal would be O(n*k): a heap-free merge sort on the scratch list keeps it O(n log n) */
+    int32_t width, a;
+    act_t *src = c, *dst = w->tmp;
+    for (width = 1; width < n; width *= 2) {
+      for (a = 0; a < n; a += 2 * width) {
+        int32_t l = a, r = a + width, le = r < n ? r : n, re = a + 2 * width < n ? a + 2 * width : n, o = a;
+        while (l < le && r < re) dst[o++] = pop_before(w, &src[r], &src[l]) ? src[r++] : src[l++];
+        while (l < le) dst[o++] = src[l++];
+        while (r < re) dst[o++] = src[r++];
+      }
+      { act_t *t = src; src = dst; dst = t; }
+    }
+    if (src != c) memcpy(c, src, sizeof(act_t) * (size_t)n);
+    return want;
+  }
+
+  /* ORACLE_TIES_REFERENCE: the selection of lib/GKlib/fkvkselect.c:22-60, step by step -- three-way pivot choice
+     between the ends and the middle, pivot parked at the right end, one left-to-right pass that moves every key
+     >= pivot to the front, then the side that contains position `want` is searched again. */
+  {
+    int32_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+      int32_t mid = lo + ((hi - lo) >> 1), store, scan;
+      act_t t;
+      float pivot;
+      if (c[lo].key < c[mid].key) mid = lo;
+      if (c[hi].key > c[mid].key) {
+        mid = hi;
+        if (c[lo].key < c[mid].key) mid = lo;
+      }
+      t = c[mid];
+      c[mid] = c[hi];
+      c[hi] = t;
+      pivot = c[hi].key;
+      store = lo - 1;
+      for (scan = lo; scan < hi; scan++) {
+        if (c[scan].key >= pivot) {
+          store++;
+          t = c[store];
+          c[store] = c[scan];
+          c[scan] = t;
+        }
+      }
+      store++;
+      t = c[store];
+      c[store] = c[hi];
+      c[hi] = t;
+      if (store > want) hi = store - 1;
+      else if (store < want) lo = store + 1;
+      else break;
+    }
+  }
+  return want;
+}
 
 static int32_t solve_column(const oracle_csc_t *m, const oracle_params_t *p, int32_t jc,
                             int32_t incols, const int64_t *icolptr, const int32_t *icolind,
@@ -166,13 +281,36 @@ static int32_t solve_column(const oracle_csc_t *m, const oracle_params_t *p, int
       ip += m->colval ? m->colval[k] * w->y[m->colind[k]] : w->y[m->colind[k]];
     w->aty[i] = ip;
   }
-  for (i = 0; i < ncols; i++) {
-    if (w->aty[i] > l1r && i != jc) {
-      w->act[na].val = i;
-      w->act[na].key = (float)w->aty[i];
-      na++;
-      w->x[i] = -0.1; /* estimate.c:440 flag */
-      actnnz += m->colptr[i + 1] - m->colptr[i];
+  if (p->nnbrs > 0) {
+    /* fSLIM, estimate.c:424-431: the active set is the neighbour list, WITHOUT the > l1r filter, keys = (float)ATy.
+       No x = -0.1 flags are set on this branch, so a warm-start model is ignored (estimate.c:453-464 writes 0.0). */
+    na = find_neighbors(m, p, jc, w);
+    for (i = 0; i < na; i++) {
+      w->act[i].val = w->cand[i].val;
+      w->act[i].key = (float)w->aty[w->cand[i].val];
+      actnnz += m->colptr[w->cand[i].val + 1] - m->colptr[w->cand[i].val];
+    }
+    if (p->order == ORACLE_ORDER_ASCENDING && na > 1) { /* the reference order is by similarity; ours is free */
+      int32_t a, b;
+      for (a = 1; a < na; a++) {
+        act_t key = w->act[a];
+        b = a - 1;
+        while (b >= 0 && w->act[b].val > key.val) {
+          w->act[b + 1] = w->act[b];
+          b--;
+        }
+        w->act[b + 1] = key;
+      }
+    }
+  } else {
+    for (i = 0; i < ncols; i++) {
+      if (w->aty[i] > l1r && i != jc) {
+        w->act[na].val = i;
+        w->act[na].key = (float)w->aty[i];
+        na++;
+        w->x[i] = -0.1; /* estimate.c:440 flag */
+        actnnz += m->colptr[i + 1] - m->colptr[i];
+      }
     }
   }
 
@@ -322,7 +460,7 @@ int oracle_learn(const oracle_csc_t *m, const oracle_params_t *p, const int32_t 
       a = (double)(m->colptr[s + 1] - m->colptr[s]);
     csq[s] = a;
   }
-  if (p->order == ORACLE_ORDER_POPULARITY) {
+  if (p->order == ORACLE_ORDER_POPULARITY || (p->nnbrs > 0 && p->nbr_ties == ORACLE_TIES_POPULARITY)) {
     /* rank[i] = position of item i when items are sorted by (descending nnz, ascending id):
        counting sort over the column lengths, stable in the id */
     int64_t maxc = 0, *start;
@@ -358,6 +496,9 @@ int oracle_learn(const oracle_csc_t *m, const oracle_params_t *p, const int32_t 
     w.tmp = (act_t *)malloc(sizeof(act_t) * (size_t)(ncols > 0 ? ncols : 1));
     w.csq = csq;
     w.rank = rank;
+    w.marker = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ncols > 0 ? ncols : 1));
+    w.cand = (act_t *)malloc(sizeof(act_t) * (size_t)(ncols > 0 ? ncols : 1));
+    memset(w.marker, 0xff, sizeof(int32_t) * (size_t)(ncols > 0 ? ncols : 1));
 
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 1)
@@ -392,6 +533,8 @@ int oracle_learn(const oracle_csc_t *m, const oracle_params_t *p, const int32_t 
     free(w.yhat);
     free(w.act);
     free(w.tmp);
+    free(w.marker);
+    free(w.cand);
     free(tind);
     free(tval);
   }

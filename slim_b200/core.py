@@ -352,6 +352,12 @@ class Staged:
         assert self._lib.SLIMB200_MatrixGramInfo(self.handle, C.byref(eb), C.byref(ms)) == SLIM_OK
         return eb.value, ms.value
 
+    def gram_layout(self):
+        """(bytes in HBM, first 16-bit column, first 8-bit column) of the staged Gram matrix (packed layout)."""
+        b, h32, h16 = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        assert self._lib.SLIMB200_MatrixGramLayout(self.handle, C.byref(b), C.byref(h32), C.byref(h16)) == SLIM_OK
+        return b.value, h32.value, h16.value
+
     def gram(self):
         """Dense copy of the staged Gram matrix (internal item order), None when it was not staged."""
         eb, _ = self.gram_info()

@@ -114,7 +114,7 @@ Options decode(const int32_t *io, const double *dopt) {
 // PrintParams, src/libslim/api.c:251-281
 void print_params(const Options &p) {
   printf(" Runtime parameters:\n");
-  printf("   Model type: SLIM\n");
+  printf("   Model type: %s\n", (p.nnbrs > 0 && p.ordered == 0) ? "fSLIM" : "SLIM");
   printf("   Optimization: l1r: %.2le, l2r: %.2le\n                 optTol: %.2le, maxniters: %d\n", p.l1r,
          p.l2r, p.opttol, p.maxniters);
   printf("   nthreads: %d\n\n", p.nthreads);
@@ -129,15 +129,30 @@ int env_device() {
   return (v && *v) ? atoi(v) : 0;
 }
 
-// `ordered` only changes the model-type label of the reference when nnbrs == 0 (api.c:54-60): the learner is the
-// same SLIM path, so it is accepted and ignored.
+// Model types of the reference (api.c:54-60): nnbrs > 0 with ordered == 0 is fSLIM; `ordered` alone only changes a
+// label, and nnbrs > 0 with ordered == 1 ("OFSLIM") runs the plain SLIM path in EstimateModelCD, which tests for
+// SLIM_MTYPE_FSLIM only (estimate.c:396, 424).  Same here.
 bool supported(const Options &p, int32_t *status) {
-  if (p.algo != SLIM_ALGO_CD || p.nnbrs != 0) {
-    fprintf(stderr, "libslim (slim-b200): only algo=cd with nnbrs=0 is implemented on the GPU engine\n");
+  if (p.algo != SLIM_ALGO_CD) {
+    fprintf(stderr, "libslim (slim-b200): only algo=cd is implemented on the GPU engine (ADMM needs MKL in the reference)\n");
+    if (status) *status = SLIM_ERROR_INPUT;
+    return false;
+  }
+  if (p.nnbrs > 0 && (p.simtype < SLIM_SIMTYPE_COS || p.simtype > SLIM_SIMTYPE_DOTP)) {
+    fprintf(stderr, "libslim (slim-b200): unknown similarity measure %d\n", p.simtype);
     if (status) *status = SLIM_ERROR_INPUT;
     return false;
   }
   return true;
+}
+
+LearnParams learn_params(const Options &p, double l1r, double l2r) {
+  LearnParams lp{l1r, l2r, p.opttol, p.maxniters, p.dbglvl};
+  if (p.nnbrs > 0 && p.ordered == 0) {
+    lp.nnbrs = p.nnbrs;
+    lp.simtype = p.simtype;
+  }
+  return lp;
 }
 
 CsrHandle *assemble(int32_t nitems, const int64_t *colptr, const int32_t *colind, const float *colval) {
@@ -361,7 +376,7 @@ CsrHandle *learn_entry(int32_t nrows, const ssize_t *rowptr, const int32_t *rowi
   }
   if (p.dbglvl & SLIM_DBG_INFO) print_params(p);
 
-  LearnParams lp{p.l1r, p.l2r, p.opttol, p.maxniters, p.dbglvl};
+  const LearnParams lp = learn_params(p, p.l1r, p.l2r);
   WarmStart ws{};
   const WarmStart *wsp = nullptr;
   if (imodel && imodel->colptr) {
@@ -516,21 +531,104 @@ int32_t recommend_1vsk(const CsrHandle *w, int32_t nratings, const int32_t *item
   return n;
 }
 
+// Descending sort by frequency with the tie order of the reference.  SLIM_DetermineHeadAndTail sorts its
+// (count, item) pairs with gk_ikvsortd (lib/GKlib/sort.c:256-261), GKlib's instance of the classic libc quicksort
+// (lib/GKlib/gk_mksort.h:118-275): median-of-three partitioning with an explicit stack, partitions of at most 8
+// elements left to one closing insertion sort.  It is not stable, and items with equal counts around the 50 % mark
+// decide which items are "head" -- so the same sequence of comparisons and swaps is followed here, on indices.
+struct FreqItem {
+  int64_t key;
+  int32_t val;
+};
+
+void sort_by_frequency_like_reference(std::vector<FreqItem> &a) {
+  const ptrdiff_t n = (ptrdiff_t)a.size();
+  if (n < 1) return;
+  auto before = [&](ptrdiff_t x, ptrdiff_t y) { return a[x].key > a[y].key; };  // "less than" of a descending sort
+  constexpr ptrdiff_t kSmall = 8;
+  if (n > kSmall) {
+    ptrdiff_t lo = 0, hi = n - 1;
+    std::vector<std::pair<ptrdiff_t, ptrdiff_t>> todo;
+    for (bool more = true; more;) {
+      ptrdiff_t mid = lo + ((hi - lo) >> 1);
+      if (before(mid, lo)) std::swap(a[mid], a[lo]);
+      if (before(hi, mid)) {
+        std::swap(a[mid], a[hi]);
+        if (before(mid, lo)) std::swap(a[mid], a[lo]);
+      }
+      ptrdiff_t left = lo + 1, right = hi - 1;
+      do {
+        while (before(left, mid)) ++left;
+        while (before(mid, right)) --right;
+        if (left < right) {
+          std::swap(a[left], a[right]);
+          if (mid == left) mid = right;
+          else if (mid == right) mid = left;
+          ++left;
+          --right;
+        } else if (left == right) {
+          ++left;
+          --right;
+          break;
+        }
+      } while (left <= right);
+      // continue with the smaller side, remember the larger one; sides of at most kSmall elements are skipped
+      const bool small_l = right - lo <= kSmall, small_r = hi - left <= kSmall;
+      if (small_l && small_r) {
+        if (todo.empty()) {
+          more = false;
+        } else {
+          lo = todo.back().first;
+          hi = todo.back().second;
+          todo.pop_back();
+        }
+      } else if (small_l) {
+        lo = left;
+      } else if (small_r) {
+        hi = right;
+      } else if (right - lo > hi - left) {
+        todo.emplace_back(lo, right);
+        lo = left;
+      } else {
+        todo.emplace_back(left, hi);
+        hi = right;
+      }
+    }
+  }
+  // closing insertion sort; the first of the leading kSmall + 1 elements in sort order becomes the sentinel at [0]
+  const ptrdiff_t end = n - 1, thresh = std::min<ptrdiff_t>(kSmall, end);
+  ptrdiff_t first = 0;
+  for (ptrdiff_t run = 1; run <= thresh; ++run)
+    if (before(run, first)) first = run;
+  if (first != 0) std::swap(a[first], a[0]);
+  for (ptrdiff_t run = 2; run <= end; ++run) {
+    ptrdiff_t pos = run - 1;
+    while (before(run, pos)) --pos;
+    ++pos;
+    if (pos != run) {
+      const FreqItem hold = a[run];
+      for (ptrdiff_t k = run; k > pos; --k) a[k] = a[k - 1];
+      a[pos] = hold;
+    }
+  }
+}
+
+// SLIM_DetermineHeadAndTail, src/libslim/api.c:215-245
 int32_t *head_and_tail(int32_t nrows, int32_t ncols, const ssize_t *rowptr, const int32_t *rowind) {
   int32_t *fm = xmalloc<int32_t>(ncols);
   if (!fm) return nullptr;
-  std::vector<std::pair<int64_t, int32_t>> cand((size_t)std::max(ncols, 0));
+  std::vector<FreqItem> cand((size_t)std::max(ncols, 0));
   for (int32_t c = 0; c < ncols; c++) {
     fm[c] = 1;
-    cand[c] = {0, c};
+    cand[c] = FreqItem{0, c};
   }
   for (ssize_t k = 0; k < rowptr[nrows]; k++)
-    if (rowind[k] >= 0 && rowind[k] < ncols) cand[rowind[k]].first++;
-  std::stable_sort(cand.begin(), cand.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+    if (rowind[k] >= 0 && rowind[k] < ncols) cand[rowind[k]].key++;
+  sort_by_frequency_like_reference(cand);
   ssize_t left = rowptr[nrows] / 2;
   for (int32_t c = 0; c < ncols && left > 0; c++) {
-    fm[cand[c].second] = 0;
-    left -= cand[c].first;
+    fm[cand[c].val] = 0;
+    left -= cand[c].key;
   }
   return fm;
 }
@@ -847,7 +945,7 @@ int32_t Py_SLIM_Mselect(slim_t *trnhandle, slim_t *tsthandle, int32_t *ioptions,
       doptions[SLIM_OPTION_L1R] = arrayl1[i1];
       doptions[SLIM_OPTION_L2R] = arrayl2[i2];
       const double t0 = now_s();
-      LearnParams lp{arrayl1[i1], arrayl2[i2], p.opttol, p.maxniters, p.dbglvl};
+      const LearnParams lp = learn_params(p, arrayl1[i1], arrayl2[i2]);
       WarmStart ws{};
       if (model) ws = WarmStart{model->ncols, model->colptr, model->colind, model->colval};
       printf("Using Coordinate Descent! \n");
@@ -1012,6 +1110,12 @@ int32_t SLIMB200_MatrixGramInfo(const slimb200_matrix_t *matrix, int32_t *elem_b
   return SLIM_OK;
 }
 
+int32_t SLIMB200_MatrixGramLayout(const slimb200_matrix_t *matrix, int64_t *bytes, int32_t *h32, int32_t *h16) {
+  if (!matrix) return SLIM_ERROR_INPUT;
+  matrix_gram_layout(reinterpret_cast<const Matrix *>(matrix), bytes, h32, h16);
+  return SLIM_OK;
+}
+
 int32_t SLIMB200_MatrixGram(const slimb200_matrix_t *matrix, void *out) {
   if (!matrix || !out) return SLIM_ERROR_INPUT;
   return matrix_gram_to_host(reinterpret_cast<const Matrix *>(matrix), out);
@@ -1024,7 +1128,7 @@ slimb200_result_t *SLIMB200_LearnColumns(slimb200_matrix_t *matrix, const int32_
   if (!matrix) return nullptr;
   const Options p = decode(ioptions, doptions);
   if (!supported(p, r_status)) return nullptr;
-  LearnParams lp{p.l1r, p.l2r, p.opttol, p.maxniters, p.dbglvl};
+  const LearnParams lp = learn_params(p, p.l1r, p.l2r);
   const CsrHandle *im = static_cast<const CsrHandle *>(imodel);
   WarmStart ws{};
   if (im && im->colptr) ws = WarmStart{im->ncols, im->colptr, im->colind, im->colval};

@@ -30,6 +30,7 @@
 #include <numeric>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <dlfcn.h>
@@ -164,12 +165,13 @@ struct Matrix {
   double *d_csq = nullptr;
   std::vector<int32_t> h_colcnt;
   // Gram matrix G = R^T R in internal item order (gram.cuh): the Gram-space solver reads rows of it
-  void *d_gram = nullptr;          // panel-major (gram_off()), float (exact integer sums) or double elements
+  void *d_gram = nullptr;          // panel-major; packed 8/16/32-bit unsigned (exact integer sums) or double elements
   size_t gram_ld = 0;              // ncols rounded up to whole panels (stride of item-indexed scratch arrays)
   bool gram_f64 = false;
+  size_t gram_bytes = 0;
+  int32_t gram_h32 = 0, gram_h16 = 0;      // packed layout: first 16-bit / 8-bit column (gram.cuh: GramView)
+  size_t gram_off16 = 0, gram_off8 = 0;    // packed layout: byte offsets of the 16-bit / 8-bit column ranges
   unsigned long long *d_expand = nullptr;  // per item: sum of len(row_u) over the users of the column
-  void *d_gcache = nullptr;                // row cache of the one-target Gram clusters (gram.cuh)
-  size_t gcache_bytes = 0;
   double gram_ms = 0.0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // extra streams: the Gram launches of the target classes run side by side
@@ -204,7 +206,6 @@ void free_matrix(Matrix *m) {
   cudaFree(m->d_inv);
   cudaFree(m->d_scratch);
   cudaFree(m->d_gram);
-  cudaFree(m->d_gcache);
   cudaFree(m->d_expand);
   if (m->stream2) cudaStreamDestroy(m->stream2);
   if (m->stream3) cudaStreamDestroy(m->stream3);
@@ -766,18 +767,46 @@ void matrix_gram_info(const Matrix *m, int32_t *elem_bytes, double *build_ms) {
   if (build_ms) *build_ms = m->gram_ms;
 }
 
+void matrix_gram_layout(const Matrix *m, int64_t *bytes, int32_t *h32, int32_t *h16) {
+  if (bytes) *bytes = m->d_gram ? (int64_t)m->gram_bytes : 0;
+  if (h32) *h32 = m->gram_f64 ? 0 : m->gram_h32;
+  if (h16) *h16 = m->gram_f64 ? 0 : m->gram_h16;
+}
+
+// Dense copy, ncols x ncols: double elements for the fp64 layout, float for the packed layout (every packed entry is
+// an integer below 2^24, so the float is exact).
 int matrix_gram_to_host(const Matrix *m, void *out) {
   try {
     if (!m->d_gram) throw EngineError(kErrInput, "matrix_gram_to_host: no Gram matrix was staged");
     DeviceGuard guard(m->device);
-    const size_t esz = m->gram_f64 ? 8 : 4;
     const size_t n = (size_t)m->ncols;
-    std::vector<unsigned char> tiled((m->gram_ld / kGramPW) * n * kGramPW * esz);
-    CK(cudaMemcpy(tiled.data(), m->d_gram, tiled.size(), cudaMemcpyDeviceToHost));
-    unsigned char *o = static_cast<unsigned char *>(out);
-    for (size_t k = 0; k < n; k++)
-      for (size_t i = 0; i < n; i++)
-        memcpy(o + (k * n + i) * esz, tiled.data() + gram_off(n, (int)k, (int)i) * esz, esz);
+    std::vector<unsigned char> raw(m->gram_bytes);
+    CK(cudaMemcpy(raw.data(), m->d_gram, raw.size(), cudaMemcpyDeviceToHost));
+    if (m->gram_f64) {
+      double *o = static_cast<double *>(out);
+      const double *g = reinterpret_cast<const double *>(raw.data());
+      for (size_t k = 0; k < n; k++)
+        for (size_t i = 0; i < n; i++) o[k * n + i] = g[gram_off(n, (int)k, (int)i)];
+    } else {
+      float *o = static_cast<float *>(out);
+      const size_t h32 = (size_t)m->gram_h32, h16 = (size_t)m->gram_h16;
+      for (size_t k = 0; k < n; k++)
+        for (size_t i = 0; i < n; i++) {
+          uint32_t v;
+          if (i < h32) {
+            memcpy(&v, raw.data() + ((i >> 6) * n + k) * 256 + (i & 63) * 4, 4);
+          } else if (i < h16) {
+            const size_t ii = i - h32;
+            uint16_t h;
+            memcpy(&h, raw.data() + m->gram_off16 + ((ii >> 6) * n + k) * 128 + (ii & 63) * 2, 2);
+            v = h;
+          } else {
+            const size_t ii = i - h16;
+            v = raw[m->gram_off8 + ((ii >> 6) * n + k) * 64 + (ii & 63)];
+          }
+          o[k * n + i] = (float)v;
+        }
+    }
     return kOk;
   } catch (const EngineError &e) {
     g_last_error = e.what();
@@ -879,6 +908,10 @@ struct SolveArgs {
   double *st_obj;
   float *st_phase;  // [ntargets][4] microseconds: candidates, active set, sweeps, epilogue (cluster kernel)
   int32_t *st_ngroups;
+  // fSLIM: neighbour lists built by fslim_neighbors_kernel (fslim.cuh), nullptr for plain SLIM
+  int32_t nnbrs;
+  const int32_t *nbr_list;  // [ntargets][nnbrs] internal ids, ascending
+  const int32_t *nbr_cnt;   // [ntargets]
 };
 
 template <int NT>
@@ -2461,6 +2494,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
 
 #include "gram.cuh"
 #include "gram_batch.cuh"
+#include "fslim.cuh"
 #include "predict.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -2475,34 +2509,59 @@ static void build_gram(Matrix *m) {
   const int32_t ncols = m->ncols;
   if (ncols <= 0 || m->nnz <= 0 || !env_int("SLIMB200_GRAM", 1)) return;
   cudaStream_t s = m->stream;
-  // element type: fp32 sums are exact iff the ratings are integers and no sum can reach 2^24
-  bool exact32 = true;
+  // Element type (gram.cuh): packed unsigned integers when every rating is a non-negative integer and no sum can
+  // reach 2^24 (in-block tiles are held as float); fp64 otherwise.
+  bool packed = true;
+  int32_t rmax = 1;
   const bool kv = m->has_val && !m->unit;
   if (kv) {
     DevBuf<int32_t> d_flag;
-    d_flag.alloc_zero(1, s);
+    d_flag.alloc_zero(2, s);
     integer_values_kernel<<<grid_for(m->nnz, 256, m->sm_count), 256, 0, s>>>(m->d_rowval, m->nnz, d_flag.p);
     m->stage_launches++;
-    int32_t flag = 1;
-    CK(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    int32_t flag[2] = {1, 0};
+    CK(cudaMemcpyAsync(flag, d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    exact32 = flag == 0;
+    packed = flag[0] == 0;
+    rmax = std::max(1, flag[1]);
   }
-  if (exact32) {
-    std::vector<double> csq(ncols);
-    CK(cudaMemcpyAsync(csq.data(), m->d_csq, sizeof(double) * ncols, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+  std::vector<double> csq(ncols);
+  CK(cudaMemcpyAsync(csq.data(), m->d_csq, sizeof(double) * ncols, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (packed) {
     double mx = 0.0;
     for (double v : csq) mx = std::max(mx, v);
-    exact32 = mx < 16777216.0;  // |G[i][k]| <= sqrt(csq_i csq_k) <= max csq (Cauchy-Schwarz), also every partial sum
+    packed = mx < 16777216.0;  // |G[i][k]| <= sqrt(csq_i csq_k) <= max csq (Cauchy-Schwarz), also every partial sum
   }
-  if (env_int("SLIMB200_GRAM_F64", 0)) exact32 = false;
-  const size_t esz = exact32 ? sizeof(float) : sizeof(double);
-  const size_t ld = ((size_t)ncols + 127) & ~size_t(127);  // item-space blocks of up to 128 columns stay inside a row
-  const size_t bytes = (ld / kGramPW) * (size_t)ncols * kGramPW * esz;  // whole panels of ncols rows
+  if (env_int("SLIMB200_GRAM_F64", 0)) packed = false;
+  const size_t ld = ((size_t)ncols + 127) & ~size_t(127);  // item-indexed scratch arrays: whole panels
+  const size_t npan = ld / kGramPW;
+  // column ranges of the packed layout: G[k][i] <= rmax * sum_u r_ui <= rmax * csq_i (integers: r <= r^2); the
+  // 16-bit range starts at the first panel from which every column's bound is <= 65535, the 8-bit range likewise
+  size_t h32 = 0, h16 = 0;
+  if (packed) {
+    int32_t last16 = -1, last8 = -1;  // last column whose bound exceeds the 16-bit / 8-bit limit
+    for (int32_t i = 0; i < ncols; i++) {
+      const double bound = (double)rmax * csq[i];
+      if (bound > 65535.0) last16 = i;
+      if (bound > 255.0) last8 = i;
+    }
+    h32 = (size_t)((last16 + 1 + kGramPW - 1) / kGramPW) * kGramPW;
+    h16 = (size_t)((last8 + 1 + kGramPW - 1) / kGramPW) * kGramPW;
+    const int force = env_int("SLIMB200_GRAM_WIDTH", 0);  // tests: 4 = everything 32-bit, 2 = no 8-bit range
+    if (force == 4) h32 = h16 = ld;
+    if (force == 2) h16 = ld;
+    h32 = std::min(h32, ld);
+    h16 = std::min(std::max(h16, h32), ld);
+  }
+  const size_t nr = (size_t)ncols;
+  const size_t off16 = (h32 / kGramPW) * nr * (kGramPW * 4);
+  const size_t off8 = off16 + ((h16 - h32) / kGramPW) * nr * (kGramPW * 2);
+  const size_t bytes = packed ? off8 + ((ld - h16) / kGramPW) * nr * kGramPW + 16  // (+16: word loads at the very end)
+                              : npan * nr * kGramPW * sizeof(double);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t budget = (size_t)env_int("SLIMB200_GRAM_GB", 100) << 30;
+  const size_t budget = (size_t)env_int("SLIMB200_GRAM_GB", 120) << 30;
   // leave room for the solve scratch and the result pools
   const size_t reserve = (size_t)16 << 30;
   if (bytes > budget || bytes + std::min(reserve, total_b / 4) > free_b) {
@@ -2522,7 +2581,13 @@ static void build_gram(Matrix *m) {
   CK(cudaMalloc(&m->d_expand, sizeof(unsigned long long) * ncols));
   CK(cudaMemsetAsync(m->d_expand, 0, sizeof(unsigned long long) * ncols, s));
   m->gram_ld = ld;
-  m->gram_f64 = !exact32;
+  m->gram_f64 = !packed;
+  m->gram_bytes = bytes;
+  m->gram_h32 = (int32_t)h32;
+  m->gram_h16 = (int32_t)h16;
+  m->gram_off16 = off16;
+  m->gram_off8 = off8;
+  GramView gv{static_cast<const unsigned char *>(m->d_gram), nr, m->gram_h32, m->gram_h16, off16, off8};
   // work items (column, entry range), heaviest columns first (internal ids are in popularity order)
   constexpr int32_t kSeg = 2048;
   std::vector<int32_t> wc, w0, w1;
@@ -2542,14 +2607,13 @@ static void build_gram(Matrix *m) {
     CK(cudaMemcpyAsync(d_w0.p, w0.data(), sizeof(int32_t) * nwork, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_w1.p, w1.data(), sizeof(int32_t) * nwork, cudaMemcpyHostToDevice, s));
     const int grid = std::max(1, std::min(nwork, m->sm_count * 8));
-#define SLIM_GRAM_BUILD(GT, HV)                                                                              \
-  gram_build_kernel<GT, HV><<<grid, 256, 0, s>>>(nwork, d_wc.p, d_w0.p, d_w1.p, m->d_colptr, m->d_colind,      \
-                                                 m->d_colval, m->d_rowptr, m->d_rowind, m->d_rowval,         \
-                                                 static_cast<GT *>(m->d_gram), (size_t)ncols, m->d_expand)
-    if (exact32) {
-      if (kv) SLIM_GRAM_BUILD(float, true); else SLIM_GRAM_BUILD(float, false);
+#define SLIM_GRAM_BUILD(GB, HV)                                                                               \
+  gram_build_kernel<GB, HV><<<grid, 256, 0, s>>>(nwork, d_wc.p, d_w0.p, d_w1.p, m->d_colptr, m->d_colind,      \
+                                                 m->d_colval, m->d_rowptr, m->d_rowind, m->d_rowval, gv, m->d_expand)
+    if (packed) {
+      if (kv) SLIM_GRAM_BUILD(GbPacked, true); else SLIM_GRAM_BUILD(GbPacked, false);
     } else {
-      if (kv) SLIM_GRAM_BUILD(double, true); else SLIM_GRAM_BUILD(double, false);
+      if (kv) SLIM_GRAM_BUILD(GbF64, true); else SLIM_GRAM_BUILD(GbF64, false);
     }
 #undef SLIM_GRAM_BUILD
     CK(cudaGetLastError());
@@ -2561,8 +2625,9 @@ static void build_gram(Matrix *m) {
   CK(cudaEventElapsedTime(&ms, g0, g1));
   m->gram_ms = ms;
   if (env_int("SLIMB200_VERBOSE", 0))
-    fprintf(stderr, "[slim-b200] Gram matrix: %d x %zu %s, %.2f GB, %d work items, built in %.1f ms\n", ncols, ld,
-            exact32 ? "fp32 (exact)" : "fp64", bytes / 1e9, nwork, ms);
+    fprintf(stderr, "[slim-b200] Gram matrix: %d x %zu %s, %.2f GB (32-bit columns %zu, 16-bit %zu, 8-bit %zu), %d work "
+                    "items, built in %.1f ms\n", ncols, ld, packed ? "packed unsigned (exact)" : "fp64", bytes / 1e9,
+            packed ? h32 : 0, packed ? h16 - h32 : 0, packed ? ld - h16 : 0, nwork, ms);
 }
 
 // K3 (second half): ordered gather of the solved columns into compact CSC arrays (the CSC
@@ -2764,9 +2829,9 @@ static int cluster_dispatch(bool vals, bool window, const SolveArgs &args, const
 
 // Launch (or, with query_only, size) cd_gram_kernel<GT, CS>.  Query: CTAs per SM for CS == 1, co-resident
 // clusters on the device for CS > 1.  `count` = CTAs (CS == 1) or clusters (CS > 1) to launch.
-template <typename GT, int CS>
+template <typename GA, int CS>
 static int gram_launch_t(const SolveArgs &args, const GramArgs &gargs, int count, cudaStream_t s, bool query_only) {
-  auto kern = cd_gram_kernel<GT, CS>;
+  auto kern = cd_gram_kernel<GA, CS>;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -2794,8 +2859,8 @@ static int gram_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &
                        bool query_only) {
 #define SLIM_GRAM_CS(CSV)                                                                        \
   if (cs == CSV)                                                                                 \
-    return f64 ? gram_launch_t<double, CSV>(args, gargs, count, s, query_only)                   \
-               : gram_launch_t<float, CSV>(args, gargs, count, s, query_only);
+    return f64 ? gram_launch_t<GaF64, CSV>(args, gargs, count, s, query_only)                    \
+               : gram_launch_t<GaPacked, CSV>(args, gargs, count, s, query_only);
   SLIM_GRAM_CS(1)
   SLIM_GRAM_CS(2)
   SLIM_GRAM_CS(4)
@@ -2807,11 +2872,12 @@ static int gram_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &
 
 constexpr int kBatchT = 8, kBatchV = 2;
 
-template <typename GT, int CS, int NTB>
+template <typename GA, int CS, int NTB>
 static int batch_launch_t(const SolveArgs &args, const GramArgs &gargs, const BatchArgs &bargs, int count,
                           cudaStream_t s, bool query_only) {
-  auto kern = cd_gram_batch_kernel<GT, CS, kBatchT, kBatchV, NTB>;
-  const size_t dyn = sizeof(BatchSmem<GT, CS, kBatchT, kBatchV, NTB>);
+  auto kern = bargs.use_mma ? cd_gram_batch_kernel<GA, CS, kBatchT, kBatchV, NTB, true>
+                            : cd_gram_batch_kernel<GA, CS, kBatchT, kBatchV, NTB, false>;
+  const size_t dyn = sizeof(BatchSmem<GA, CS, kBatchT, kBatchV, NTB>);
   constexpr int kBatchNT = NTB;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -2843,9 +2909,9 @@ static int batch_launch(bool f64, int cs, int nt, const SolveArgs &args, const G
   // fp64 G: the staging ring of 16 warps would not fit shared memory, 256 threads only
 #define SLIM_BATCH_CS(CSV)                                                                         \
   if (cs == CSV) {                                                                                 \
-    if (f64) return batch_launch_t<double, CSV, 256>(args, gargs, bargs, count, s, query_only);    \
-    return nt == 512 ? batch_launch_t<float, CSV, 512>(args, gargs, bargs, count, s, query_only)   \
-                     : batch_launch_t<float, CSV, 256>(args, gargs, bargs, count, s, query_only);  \
+    if (f64) return batch_launch_t<GaF64, CSV, 256>(args, gargs, bargs, count, s, query_only);     \
+    return nt == 512 ? batch_launch_t<GaPacked, CSV, 512>(args, gargs, bargs, count, s, query_only) \
+                     : batch_launch_t<GaPacked, CSV, 256>(args, gargs, bargs, count, s, query_only); \
   }
   SLIM_BATCH_CS(1)
   SLIM_BATCH_CS(4)
@@ -2903,6 +2969,11 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     // ---- launch plan ---------------------------------------------------------------------------
     // Gram-space solver whenever G was staged (gram.cuh); otherwise the user-space kernels below
     const bool use_gram = m->d_gram != nullptr && env_int("SLIMB200_GRAM", 1) != 0;
+    const bool fslim = p.nnbrs > 0;
+    if (fslim && !use_gram)
+      throw EngineError(kErrInput, "learn: fSLIM (nnbrs > 0) needs the Gram-space solver, but no Gram matrix is staged "
+                                   "for this training matrix (too many items for HBM, or SLIMB200_GRAM=0)");
+    if (fslim && (p.simtype < 0 || p.simtype > 2)) throw EngineError(kErrInput, "learn: unknown simtype");
     const bool kernel_vals = m->has_val && !m->unit;
     LaunchPlan plan{};
     const double mean_col = ncols > 0 ? (double)m->nnz / ncols : 0.0;
@@ -2971,6 +3042,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     //   the rest          : cd_gram_kernel, one CTA per target
     GramArgs gargs{};
     BatchArgs bargs{};
+    bargs.use_mma = env_int("SLIMB200_BATCH_MMA", 1) != 0;
     struct GramClass {
       bool batch;
       int cs, nt;      // CTAs per cluster, threads per CTA
@@ -2983,12 +3055,13 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     if (use_gram) {
       int gram_cs = env_int("SLIMB200_GRAM_CS", 4);
       if (gram_cs != 1 && gram_cs != 2 && gram_cs != 4 && gram_cs != 8 && gram_cs != 16) gram_cs = 4;
-      const int gram_heavy = env_int("SLIMB200_GRAM_HEAVY", 2000);
+      // fSLIM targets have at most nnbrs active coordinates: one CTA each
+      const int gram_heavy = fslim ? INT32_MAX : env_int("SLIMB200_GRAM_HEAVY", 2000);
       // measured on C4 (profiles/r01_gram_class_routing.txt): below ~30K nonzeros a batch of 8 targets costs more
       // SM-seconds than eight one-target clusters (the union nonzero list is much longer than each target's own and
       // the item-space blocks cover inactive coordinates), so by default the two batch classes coincide
-      const int gram_batch = std::max(gram_heavy, env_int("SLIMB200_GRAM_BATCH", 30000));
-      const int gram_top = std::max(gram_batch, env_int("SLIMB200_GRAM_TOP", 30000));
+      const int gram_batch = fslim ? INT32_MAX : std::max(gram_heavy, env_int("SLIMB200_GRAM_BATCH", 30000));
+      const int gram_top = fslim ? INT32_MAX : std::max(gram_batch, env_int("SLIMB200_GRAM_TOP", 30000));
       int32_t ntop = 0;
       for (int32_t q = 0; q < nsel; q++)
         if (m->h_colcnt[m->h_rank[colof(q)]] >= gram_top) ntop++;
@@ -3014,6 +3087,11 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       }
       int slots = 0;
       for (auto &gc : classes) {
+        if (gc.ntargets == 0) {  // nothing to launch for this class: no occupancy query either
+          gc.units = 0;
+          gc.slot_base = slots;
+          continue;
+        }
         int hw = gc.batch ? batch_launch(m->gram_f64, gc.cs, gc.nt, args, gargs, bargs, 1, s, true)
                           : gram_launch(m->gram_f64, gc.cs, args, gargs, 1, s, true);
         if (gc.cs == 1) hw *= m->sm_count;
@@ -3024,7 +3102,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         slots += gc.units * gc.cs;
         if (env_int("SLIMB200_VERBOSE", 0) && gc.ntargets > 0)
           fprintf(stderr, "[slim-b200] Gram-space (%s G): %d targets with nnz >= %d -> %s, %d x (%d CTAs x %d threads)\n",
-                  m->gram_f64 ? "fp64" : "fp32", gc.ntargets, gc.min_nnz,
+                  m->gram_f64 ? "fp64" : "packed", gc.ntargets, gc.min_nnz,
                   gc.batch ? "cd_gram_batch_kernel (8 targets per cluster)" : "cd_gram_kernel", gc.units, gc.cs, gc.nt);
       }
       plan.grid = std::max(1, slots);
@@ -3048,8 +3126,6 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     const size_t o_gslot = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
     const size_t o_grow = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
     const size_t o_gval = carve(use_gram ? g * col_stride * sizeof(double) : 0);
-    const size_t o_gcpp = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
-    const size_t o_gcps = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
     size_t nbcta = 0;  // the batch classes come first: their CTAs use slots 0 .. nbcta-1
     for (const auto &gc : classes)
       if (gc.batch) nbcta += (size_t)gc.units * gc.cs;
@@ -3123,52 +3199,14 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     cargs.grp_stride = grp_stride;
     args.act_idx = reinterpret_cast<int32_t *>(sb + o_idx);
     if (use_gram) {
-      gargs.G = m->d_gram;
-      gargs.nr = (size_t)ncols;
+      gargs.gv = GramView{static_cast<const unsigned char *>(m->d_gram), (size_t)ncols, m->gram_h32, m->gram_h16,
+                          m->gram_off16, m->gram_off8};
       gargs.act = reinterpret_cast<int32_t *>(sb + o_idx);
       gargs.x = reinterpret_cast<double *>(sb + o_x);
       gargs.slotp = reinterpret_cast<int32_t *>(sb + o_gslot);
       gargs.sl_row = reinterpret_cast<int32_t *>(sb + o_grow);
       gargs.sl_val = reinterpret_cast<double *>(sb + o_gval);
       gargs.expand = m->d_expand;
-      gargs.cposp = reinterpret_cast<int32_t *>(sb + o_gcpp);
-      gargs.sl_cpos = reinterpret_cast<int32_t *>(sb + o_gcps);
-      // row cache for the one-target cluster class: SLIMB200_GRAM_CACHE_MB per cluster (default 0 = off: measured
-      // neutral on C4, profiles/r01_gram_class_routing.txt),
-      // shrunk to what is free (another staged matrix may hold its own G and cache)
-      gargs.cache = nullptr;
-      gargs.cache_elems = 0;
-      int cache_clusters = 0;
-      for (const auto &gc : classes)
-        if (!gc.batch && gc.cs > 1) cache_clusters = gc.units;
-      const size_t want_mb = (size_t)std::max(0, env_int("SLIMB200_GRAM_CACHE_MB", 0));
-      if (cache_clusters > 0 && want_mb > 0) {
-        // never more than a whole target needs: every row of an all-active target
-        const size_t whole = (size_t)ncols * col_stride * (m->gram_f64 ? 8 : 4);
-        size_t need = (size_t)cache_clusters * std::min(want_mb << 20, whole);
-        if (need > m->gcache_bytes) {
-          cudaFree(m->d_gcache);
-          m->d_gcache = nullptr;
-          m->gcache_bytes = 0;
-          size_t free_b = 0, total_b = 0;
-          CK(cudaMemGetInfo(&free_b, &total_b));
-          const size_t reserve = (size_t)8 << 30;
-          const size_t avail = free_b > reserve ? free_b - reserve : 0;
-          need = std::min(need, avail);
-          if (need / cache_clusters >= (size_t)4096 && cudaMalloc(&m->d_gcache, need) == cudaSuccess)
-            m->gcache_bytes = need;
-          else
-            (void)cudaGetLastError();
-        }
-        if (m->d_gcache) {
-          const size_t esz = m->gram_f64 ? 8 : 4;
-          gargs.cache = m->d_gcache;
-          gargs.cache_elems = (std::min(m->gcache_bytes, need) / cache_clusters / esz) & ~size_t(31);
-          if (env_int("SLIMB200_VERBOSE", 0))
-            fprintf(stderr, "[slim-b200] Gram row cache: %d clusters x %.0f MB\n", cache_clusters,
-                    gargs.cache_elems * esz / 1048576.0);
-        }
-      }
       bargs.xt = reinterpret_cast<double *>(sb + o_bxt);
       bargs.sl_valT = reinterpret_cast<double *>(sb + o_bsv);
       bargs.amask = reinterpret_cast<uint32_t *>(sb + o_bam);
@@ -3253,7 +3291,46 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         args.st_ngroups = d_ng.p;
         LaunchPlan lp = plan;
         lp.grid = std::min(plan.grid, nt);
+        // fSLIM: neighbour lists of this round's targets (fslim.cuh), consumed by cd_gram_kernel
+        DevBuf<int32_t> d_nbr, d_nbrcnt, d_nq, d_ncv;
+        DevBuf<uint32_t> d_nfirst;
+        DevBuf<float> d_ndot, d_nck;
+        args.nnbrs = 0;
+        args.nbr_list = nullptr;
+        args.nbr_cnt = nullptr;
+        int nbr_grid = 0;
+        if (fslim) {
+          nbr_grid = std::max(1, std::min<int>(nt, m->sm_count * 4));
+          d_nbr.alloc((size_t)nt * p.nnbrs);
+          d_nbrcnt.alloc_zero(nt, s);
+          d_nq.alloc_zero(1, s);
+          d_nfirst.alloc((size_t)nbr_grid * col_stride);
+          CK(cudaMemsetAsync(d_nfirst.p, 0xff, sizeof(uint32_t) * (size_t)nbr_grid * col_stride, s));
+          d_ndot.alloc_zero((size_t)nbr_grid * col_stride, s);
+          d_ncv.alloc((size_t)nbr_grid * col_stride);
+          d_nck.alloc((size_t)nbr_grid * col_stride);
+          args.nnbrs = p.nnbrs;
+          args.nbr_list = d_nbr.p;
+          args.nbr_cnt = d_nbrcnt.p;
+        }
         CK(cudaEventRecord(e0, s));
+        if (fslim) {
+          NbrArgs nb{};
+          nb.nnbrs = p.nnbrs;
+          nb.simtype = p.simtype;
+          nb.queue = d_nq.p;
+          nb.first = d_nfirst.p;
+          nb.dot = d_ndot.p;
+          nb.cand_val = d_ncv.p;
+          nb.cand_key = d_nck.p;
+          nb.out_nbr = d_nbr.p;
+          nb.out_cnt = d_nbrcnt.p;
+          if (kernel_vals) fslim_neighbors_kernel<true><<<nbr_grid, kNbrNT, 0, s>>>(args, nb);
+          else fslim_neighbors_kernel<false><<<nbr_grid, kNbrNT, 0, s>>>(args, nb);
+          CK(cudaGetLastError());
+          res->tm.launches++;
+          res->tm.solve_launches++;
+        }
         if (use_gram) {
           // `pending` is sorted by descending column nnz: the classes are consecutive ranges
           cudaStream_t streams[4] = {s, m->stream2, m->stream3, m->stream4};

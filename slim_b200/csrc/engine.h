@@ -15,6 +15,10 @@ struct LearnParams {
   double l1r, l2r, opttol;
   int32_t maxniters;
   int32_t dbglvl;
+  // fSLIM (reference src/libslim/neighbors.c, estimate.c:424-431): nnbrs > 0 restricts the active set of every
+  // target to its nnbrs most similar columns; simtype as include/slim.h (0 cos, 1 jac, 2 dotp)
+  int32_t nnbrs = 0;
+  int32_t simtype = 0;
 };
 
 // Host view of a model used for warm starts: CSC of a previous W (reference
@@ -54,8 +58,12 @@ int matrix_window_gram_to_host(const Matrix *m, double *out);
 // Gram matrix G = R^T R staged for the Gram-space solver (INTERNAL item order).  elem_bytes: 0 when G
 // was not staged (too large / disabled), 4 = float (exact integer sums), 8 = double.
 void matrix_gram_info(const Matrix *m, int32_t *elem_bytes, double *build_ms);
-// Dense ncols x ncols copy (no row padding) in the element type reported above (tests).
+// Dense ncols x ncols copy (no row padding): float when elem_bytes == 4 (the packed integer layout, exact), double
+// when elem_bytes == 8 (tests).
 int matrix_gram_to_host(const Matrix *m, void *out);
+// Footprint of the staged Gram matrix in HBM and the column ranges of the packed layout: 32-bit elements for
+// columns [0, h32), 16-bit for [h32, h16), 8-bit from h16 on (zeros for the fp64 layout).
+void matrix_gram_layout(const Matrix *m, int64_t *bytes, int32_t *h32, int32_t *h16);
 
 Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel,
               const WarmStart *warm, int32_t *status);

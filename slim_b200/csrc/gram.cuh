@@ -28,11 +28,137 @@ constexpr int kGramNT = 256;
 constexpr int kGramNW = kGramNT / 32;
 constexpr int kGramUnroll = 16;  // independent gathered loads in flight per lane
 
-// (layout of G: panel-major, see kGramPW / gram_off() in engine.cu)
+// ------------------------------------------------------------------------------------------------
+// Layout of G in HBM.  PANEL-major: a panel is kGramPW = 64 consecutive columns of all rows, rows contiguous
+// inside the panel, so a block of coordinates reads short segments of many rows out of ONE panel.
+//
+// Element width.  For integer, non-negative ratings every entry is a non-negative integer bounded by
+//     G[k][i] = sum_u r_uk r_ui  <=  rmax * sum_u r_ui  <=  rmax * csq_i        (r <= r^2 for integers),
+// i.e. by a per-COLUMN bound that falls with the item's popularity.  Items are stored in popularity order, so
+// the columns split into three contiguous ranges (boundaries rounded to whole panels):
+//     [0, h32)  : 32-bit unsigned     [h32, h16) : bound <= 65535, 16-bit     [h16, ld) : bound <= 255, 8-bit
+// For C4 (100 K items) that is 192 / 29 120 / 70 688 columns: 130 KB per row instead of 400 KB, 13 GB instead of
+// 40 GB, and -- what matters -- 2-3x fewer DRAM sectors per gathered block (profiles/r02_typed_gram_model.txt).
+// All sums are exact.  Ratings that are not non-negative integers (or sums >= 2^32) use fp64 elements instead.
+// ------------------------------------------------------------------------------------------------
+struct GramView {
+  const unsigned char *base;
+  size_t nr;           // rows of G (= ncols)
+  int32_t h32, h16;    // packed layout: first column of the 16-bit / 8-bit range (multiples of kGramPW)
+  size_t off16, off8;  // packed layout: byte offsets of the 16-bit / 8-bit ranges
+};
+
+// fp64 elements, one range: element (k, i) at gram_off(nr, k, i)
+struct GaF64 {
+  using Tile = double;                          // element type of the in-block Gram tiles in shared memory
+  static constexpr int kMaxRowBytes = kGramPW * 8;  // bytes of one panel row
+  struct Col {
+    const double *p;
+  };
+  static __device__ __forceinline__ Col col(const GramView &g, int i) {
+    return Col{reinterpret_cast<const double *>(g.base) + gram_off(g.nr, 0, i)};
+  }
+  using Raw = double;  // what a gathered load leaves in a register until it is consumed
+  static __device__ __forceinline__ Raw raw(const Col &c, int r) { return __ldg(c.p + (size_t)(uint32_t)r * kGramPW); }
+  static __device__ __forceinline__ double cvt(const Col &, Raw w) { return w; }
+  static __device__ __forceinline__ double at(const Col &c, int r) { return raw(c, r); }
+  static __device__ __forceinline__ double at(const GramView &g, int k, int i) {
+    return __ldg(reinterpret_cast<const double *>(g.base) + gram_off(g.nr, k, i));
+  }
+  // two adjacent items (item0 even) of row k
+  static __device__ __forceinline__ void at2(const GramView &g, int k, int item0, double (&o)[2]) {
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(g.base) + gram_off(g.nr, k, item0)));
+    o[0] = v.x;
+    o[1] = v.y;
+  }
+  static __device__ __forceinline__ int row_bytes(const GramView &, int) { return kGramPW * 8; }
+  static __device__ __forceinline__ const unsigned char *panel(const GramView &g, int item0) {
+    return g.base + gram_off(g.nr, 0, item0) * 8;
+  }
+};
+
+// packed unsigned elements, three column ranges
+struct GaPacked {
+  using Tile = float;  // exact: every entry is an integer below 2^24 ... or the tile holds it as float anyway
+  static constexpr int kMaxRowBytes = kGramPW * 4;
+  struct Col {
+    const unsigned char *p;  // 4-byte aligned address of the word that holds (row 0, column i)
+    uint32_t stride;         // bytes per panel row: 64 x element width
+    uint32_t sel;            // PRMT selector that moves the element's bytes to the bottom of a register, zero above
+  };
+  // byte offset of (row 0, column i), bytes per panel row, log2 element width
+  static __device__ __forceinline__ size_t col_byte(const GramView &g, int i, uint32_t &stride, uint32_t &wlog) {
+    if (i < g.h32) {
+      stride = kGramPW * 4;
+      wlog = 2;
+      return (size_t)(i >> 6) * g.nr * (kGramPW * 4) + (size_t)(i & 63) * 4;
+    }
+    if (i < g.h16) {
+      const int ii = i - g.h32;
+      stride = kGramPW * 2;
+      wlog = 1;
+      return g.off16 + (size_t)(ii >> 6) * g.nr * (kGramPW * 2) + (size_t)(ii & 63) * 2;
+    }
+    const int ii = i - g.h16;
+    stride = kGramPW;
+    wlog = 0;
+    return g.off8 + (size_t)(ii >> 6) * g.nr * kGramPW + (size_t)(ii & 63);
+  }
+  static __device__ __forceinline__ Col col(const GramView &g, int i) {
+    uint32_t stride, wlog;
+    const size_t byte = col_byte(g, i, stride, wlog);
+    Col c;
+    c.p = g.base + (byte & ~size_t(3));
+    c.stride = stride;
+    const uint32_t b = (uint32_t)(byte & 3);  // first byte of the element inside its word
+    // selector nibbles 0-3 pick a byte of the loaded word, 4 picks a byte of the second PRMT operand (zero)
+    c.sel = wlog == 2 ? 0x3210u : (wlog == 1 ? (0x4400u | ((b + 1) << 4) | b) : (0x4440u | b));
+    return c;
+  }
+  using Raw = uint32_t;
+  // one mad.wide (row * row bytes + column base) and one 32-bit load per gathered element
+  static __device__ __forceinline__ Raw raw(const Col &c, int r) {
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"((uint32_t)r), "r"(c.stride), "l"(c.p));
+    return __ldg(reinterpret_cast<const uint32_t *>(a));
+  }
+  static __device__ __forceinline__ double cvt(const Col &c, Raw w) { return (double)__byte_perm(w, 0u, c.sel); }
+  static __device__ __forceinline__ double at(const Col &c, int r) { return cvt(c, raw(c, r)); }
+  static __device__ __forceinline__ double at(const GramView &g, int k, int i) {
+    uint32_t stride, wlog;
+    const size_t byte = col_byte(g, i, stride, wlog) + (size_t)k * stride;
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(g.base + (byte & ~size_t(3))));
+    const uint32_t m = wlog == 2 ? 0xffffffffu : (wlog == 1 ? 0xffffu : 0xffu);
+    return (double)((w >> ((uint32_t)(byte & 3) * 8u)) & m);
+  }
+  static __device__ __forceinline__ void at2(const GramView &g, int k, int item0, double (&o)[2]) {
+    uint32_t stride, wlog;
+    const size_t byte = col_byte(g, item0, stride, wlog) + (size_t)k * stride;  // item0 even: both in one panel row
+    if (wlog == 2) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2 *>(g.base + byte));
+      o[0] = (double)v.x;
+      o[1] = (double)v.y;
+    } else if (wlog == 1) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(g.base + byte));
+      o[0] = (double)(w & 0xffffu);
+      o[1] = (double)(w >> 16);
+    } else {
+      const uint32_t w = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(g.base + byte));
+      o[0] = (double)(w & 0xffu);
+      o[1] = (double)(w >> 8);
+    }
+  }
+  static __device__ __forceinline__ int row_bytes(const GramView &g, int item0) {
+    return item0 < g.h32 ? kGramPW * 4 : (item0 < g.h16 ? kGramPW * 2 : kGramPW);
+  }
+  static __device__ __forceinline__ const unsigned char *panel(const GramView &g, int item0) {  // item0 % 64 == 0
+    uint32_t stride, wlog;
+    return g.base + col_byte(g, item0, stride, wlog);
+  }
+};
 
 struct GramArgs {
-  const void *G;  // panel-major Gram matrix, see gram_off()
-  size_t nr;      // rows of G (= ncols)
+  GramView gv;    // the Gram matrix
   int32_t q_begin, q_end;  // positions in SolveArgs::targets served by this launch
   int32_t *queue;          // work counter of this launch (starts at 0)
   int32_t slot_base;       // first scratch slot of this launch (slot = slot_base + blockIdx.x)
@@ -43,13 +169,6 @@ struct GramArgs {
   int32_t *sl_row;  // nonzero list: item id ...
   double *sl_val;   // ... and effective value (0 for a coordinate that went back to zero)
   const unsigned long long *expand;  // per item: sum of row lengths over the users of the column
-  // Row cache of the one-target cluster launch (CS > 1): the first time a coordinate becomes nonzero, its Gram
-  // row RESTRICTED TO THE ACTIVE SET is gathered once into a contiguous buffer shared by the cluster; every
-  // later block round reads 128 contiguous bytes of it instead of 32 scattered sectors of G.
-  void *cache;          // GT[clusters][cache_elems], nullptr = no cache
-  size_t cache_elems;   // elements per cluster
-  int32_t *cposp;       // per CTA, per active coordinate: its cache row or -1
-  int32_t *sl_cpos;     // per CTA, per list entry: cache row or -1
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -59,7 +178,24 @@ struct GramArgs {
 // every row reaches HBM once.  fp32 sums are exact when the ratings are integers and the largest
 // column sum of squares is below 2^24 (checked at staging); otherwise GT = double.
 // ------------------------------------------------------------------------------------------------
-template <typename GT, bool HASVAL>
+// element update of the build: fp64 atomic add, or -- packed layout -- an integer add into the 32-bit word that
+// holds the 8 / 16 / 32-bit field (no carry can leave a field: every partial sum is <= the final, bounded, sum)
+struct GbF64 {
+  static __device__ __forceinline__ void add(const GramView &g, int k, int i, float a, float b) {
+    atomicAdd(const_cast<double *>(reinterpret_cast<const double *>(g.base)) + gram_off(g.nr, k, i), (double)a * (double)b);
+  }
+};
+struct GbPacked {
+  static __device__ __forceinline__ void add(const GramView &g, int k, int i, float a, float b) {
+    uint32_t stride, wlog;
+    const size_t byte = GaPacked::col_byte(g, i, stride, wlog) + (size_t)k * stride;
+    const uint32_t inc = (uint32_t)(a * b);  // integer ratings: exact
+    atomicAdd(reinterpret_cast<uint32_t *>(const_cast<unsigned char *>(g.base) + (byte & ~size_t(3))),
+              inc << ((uint32_t)(byte & 3) * 8u));
+  }
+};
+
+template <typename GB, bool HASVAL>
 __global__ void __launch_bounds__(256) gram_build_kernel(int32_t nwork, const int32_t *__restrict__ wk_col,
                                                          const int32_t *__restrict__ wk_e0,
                                                          const int32_t *__restrict__ wk_e1,
@@ -68,7 +204,7 @@ __global__ void __launch_bounds__(256) gram_build_kernel(int32_t nwork, const in
                                                          const float *__restrict__ colval,
                                                          const int64_t *__restrict__ rowptr,
                                                          const int32_t *__restrict__ rowind,
-                                                         const float *__restrict__ rowval, GT *G, size_t nr,
+                                                         const float *__restrict__ rowval, const GramView gv,
                                                          unsigned long long *expand) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -97,8 +233,8 @@ __global__ void __launch_bounds__(256) gram_build_kernel(int32_t nwork, const in
           if (pa) ra = __ldg(rowval + ta);
           if (pb) rb = __ldg(rowval + tb);
         }
-        if (pa) atomicAdd(G + gram_off(nr, k, ia), (GT)ra * (GT)va);
-        if (pb) atomicAdd(G + gram_off(nr, k, ib), (GT)rb * (GT)vb);
+        if (pa) GB::add(gv, k, ia, ra, va);
+        if (pb) GB::add(gv, k, ib, rb, vb);
         ta += 32;
         tb += 32;
       }
@@ -111,12 +247,25 @@ __global__ void __launch_bounds__(256) gram_build_kernel(int32_t nwork, const in
   }
 }
 
-// flags bit 0: some rating is not an integer (or is not finite)
+// flags[0] bit 0: some rating is not an integer (or is not finite), bit 1: some rating is negative;
+// flags[1] = largest rating (as an integer, when they all are)
 __global__ void integer_values_kernel(const float *__restrict__ v, int64_t n, int32_t *flags) {
-  bool bad = false;
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
-    bad |= !(v[k] == rintf(v[k]) && fabsf(v[k]) < 16777216.0f);
-  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1);
+  bool bad = false, neg = false;
+  int mx = 0;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const float x = v[k];
+    const bool isint = x == rintf(x) && fabsf(x) < 16777216.0f;
+    bad |= !isint;
+    neg |= x < 0.0f;
+    if (isint) mx = max(mx, (int)x);
+  }
+  const unsigned f = (__any_sync(0xffffffffu, bad) ? 1u : 0u) | (__any_sync(0xffffffffu, neg) ? 2u : 0u);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) {
+    if (f) atomicOr(flags, (int)f);
+    atomicMax(flags + 1, mx);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -132,8 +281,6 @@ struct __align__(16) GramSmem {
   int len;    // entries in the nonzero list
   int nzero;  // ... of which currently zero
   int done;
-  int ncached;  // cache rows handed out for the current target
-  int napp;     // entries appended in the current block round
 };
 
 __device__ __forceinline__ uint32_t gram_cluster_rank() {
@@ -159,71 +306,58 @@ __device__ __forceinline__ double gram_allsum(GramSmem<CS> &sm, double v, uint32
 }
 
 // partial (this warp's share) of  sum_{e < len} val[e] * G[row[e]][col]  for the lane's column `col`.
-// CACHED: entries with sl_cpos[e] >= 0 are read from the row cache (crow = cache + block position + lane,
-// rows npad apart) through L2 (the rows were written by another CTA of the cluster).
-template <typename GT, bool CACHED>
-__device__ __forceinline__ double gram_gather_sum(const GT *__restrict__ Gcol, const int32_t *sl_row,
+// The (row, value) pairs of a 32-entry chunk are staged in this warp's slice of shared memory and read back as
+// broadcasts: per gathered element one LDS (row), one mad.wide, one LDG, one PRMT, one I2F, one LDS.64 (value) and
+// the DFMA.
+struct GatherStage {
+  int row[32];
+  double val[32];
+};
+
+template <typename GA>
+__device__ __forceinline__ double gram_gather_sum(const typename GA::Col &col, const int32_t *sl_row,
                                                   const double *sl_val, int len, int first_chunk, int chunk_stride,
-                                                  const int32_t *sl_cpos = nullptr, const GT *crow = nullptr,
-                                                  size_t npad = 0) {
+                                                  GatherStage &st) {
   const int lane = threadIdx.x & 31;
   double acc = 0.0;
   for (int c = first_chunk; c * 32 < len; c += chunk_stride) {
     const int e = c * 32 + lane;
-    int row_l = 0, cp_l = -1;
-    double val_l = 0.0;
-    if (e < len) {
-      row_l = sl_row[e];
-      val_l = sl_val[e];
-      if (CACHED) cp_l = sl_cpos[e];
-    }
+    __syncwarp();
+    st.row[lane] = e < len ? sl_row[e] : 0;
+    st.val[lane] = e < len ? sl_val[e] : 0.0;  // entries past the end contribute 0 * G[0][col]
+    __syncwarp();
     const int cnt = min(32, len - c * 32);
     for (int i0 = 0; i0 < cnt; i0 += kGramUnroll) {
-      GT g[kGramUnroll];
+      typename GA::Raw g[kGramUnroll];
 #pragma unroll
-      for (int u = 0; u < kGramUnroll; u++) {
-        const int r = __shfl_sync(0xffffffffu, row_l, (i0 + u) & 31);
-        if (CACHED) {
-          const int cp = __shfl_sync(0xffffffffu, cp_l, (i0 + u) & 31);
-          // one load instruction for both sources (L2 only: the cache rows were written by peer CTAs)
-          const GT *src = cp >= 0 ? crow + (size_t)cp * npad : Gcol + (size_t)r * kGramPW;
-          g[u] = __ldcg(src);
-        } else {
-          g[u] = __ldg(Gcol + (size_t)r * kGramPW);
-        }
-      }
+      for (int u = 0; u < kGramUnroll; u++) g[u] = GA::raw(col, st.row[i0 + u]);
 #pragma unroll
-      for (int u = 0; u < kGramUnroll; u++) {
-        const double v = __shfl_sync(0xffffffffu, val_l, (i0 + u) & 31);
-        acc = fma(v, (double)g[u], acc);
-      }
+      for (int u = 0; u < kGramUnroll; u++) acc = fma(st.val[i0 + u], GA::cvt(col, g[u]), acc);
     }
   }
   return acc;
 }
 
-template <typename GT, int CS>
+template <typename GA, int CS>
 __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, const GramArgs ga) {
   constexpr int NT = kGramNT, NW = kGramNW;
+  using Tile = typename GA::Tile;
   __shared__ GramSmem<CS> sm;
-  __shared__ GT s_gbb[32][33];
+  __shared__ Tile s_gbb[32][33];
+  __shared__ GatherStage s_stage[NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = CS > 1 ? gram_cluster_rank() : 0u;
   uint32_t tag = 0;
   int par = 0;
 
-  const GT *__restrict__ G = static_cast<const GT *>(ga.G);
-  const size_t nr = ga.nr;
+  const GramView &gv = ga.gv;
   const size_t slot = (size_t)(ga.slot_base + blockIdx.x) * a.col_stride;
   int32_t *act = ga.act + slot;
   double *x = ga.x + slot;
   int32_t *slotp = ga.slotp + slot;
   int32_t *sl_row = ga.sl_row + slot;
   double *sl_val = ga.sl_val + slot;
-  int32_t *cposp = ga.cposp + slot;
-  int32_t *sl_cpos = ga.sl_cpos + slot;
-  GT *const cache = (CS > 1 && ga.cache) ? static_cast<GT *>(ga.cache) + (size_t)(blockIdx.x / CS) * ga.cache_elems : nullptr;
   float *xw = a.xw ? a.xw + slot : nullptr;
 
   if (CS > 1) {
@@ -250,7 +384,7 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
     if (q >= ga.q_end) break;
     const int j = a.targets[q];
     const int cntj = a.colcnt[j];
-    auto gj_at = [&](int i) { return __ldg(G + gram_off(nr, j, i)); };  // aTy_i = G[j][i]
+    auto gj_at = [&](int i) { return GA::at(gv, j, i); };  // aTy_i = G[j][i]
     const bool timer = rank == 0 && tid == 0;
     unsigned long long t_start = 0, t_act = 0, t_sweep = 0;
     if (timer) t_start = globaltimer_ns();
@@ -269,20 +403,31 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
     // ---- active set: ascending i, strict aTy > l1r, i != j (estimate.c:433-444); aTy_i = G[j][i]
     int na = 0;
     long long actnnz = 0;
-    for (int base = 0; base < a.ncols; base += NT) {
-      const int i = base + tid;
-      double v = 0.0;
-      if (i < a.ncols) v = (double)gj_at(i);
-      const bool flag = (i < a.ncols) && (i != j) && (v > a.l1r);
-      int tot;
-      const int pos = na + team_excl_scan<NT>(flag, sm.sc, tot);
-      if (flag) {
-        act[pos] = i;
-        x[pos] = warm ? (double)xw[i] : 0.0;
-        cposp[pos] = -1;
+    if (a.nnbrs > 0) {
+      // fSLIM (estimate.c:424-431): the active set is the neighbour list of fslim_neighbors_kernel, no > l1r filter;
+      // the reference sets no x = -0.1 flags on this branch, so a warm-start model has no effect (estimate.c:453-464)
+      na = a.nbr_cnt[q];
+      for (int p = tid; p < na; p += NT) {
+        const int i = a.nbr_list[(size_t)q * a.nnbrs + p];
+        act[p] = i;
+        x[p] = 0.0;
         actnnz += a.colcnt[i];
       }
-      na += tot;
+    } else {
+      for (int base = 0; base < a.ncols; base += NT) {
+        const int i = base + tid;
+        double v = 0.0;
+        if (i < a.ncols) v = gj_at(i);
+        const bool flag = (i < a.ncols) && (i != j) && (v > a.l1r);
+        int tot;
+        const int pos = na + team_excl_scan<NT>(flag, sm.sc, tot);
+        if (flag) {
+          act[pos] = i;
+          x[pos] = warm ? (double)xw[i] : 0.0;
+          actnnz += a.colcnt[i];
+        }
+        na += tot;
+      }
     }
     __syncthreads();
     if (warm) {
@@ -306,7 +451,6 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
         if (flag) {
           sl_row[pos] = act[p];
           sl_val[pos] = xv;
-          sl_cpos[pos] = cposp[p];
         }
         len += tot;
       }
@@ -314,14 +458,9 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
       if (tid == 0) {
         sm.len = len;
         sm.nzero = 0;
-        sm.napp = 0;
       }
       __syncthreads();
     };
-    const size_t npad = ((size_t)na + 31) & ~size_t(31);
-    const size_t rows_fit = ga.cache_elems / (npad ? npad : 32);
-    const int rows_cap = cache ? (int)(rows_fit < (size_t)0x7fffffff ? rows_fit : (size_t)0x7fffffff) : 0;
-    if (tid == 0) sm.ncached = 0;
     rebuild_list();
 
     // ---- iteration cap (estimate.c:448-449)
@@ -341,7 +480,7 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
           const int p0 = b * 32, pm = p0 + lane;
           const bool valid = pm < na;
           const int ab = act[valid ? pm : p0];
-          const GT *__restrict__ Gab = G + gram_off(nr, 0, ab);  // column ab: row k at + k * PW
+          const typename GA::Col cab = GA::col(gv, ab);  // column ab: row k at + k * row stride
           // operands of the chain, requested early (warp 0 only uses them)
           double xv = 0.0, sq = 0.0, den = 1.0, aty = 0.0;
           int myslot = -1;
@@ -353,20 +492,17 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
             const double cn = (double)__ldg(a.cnorms + ab);
             den = cn * cn + a.l2r;
             sq = __ldg(a.csq + ab);
-            aty = (double)(float)(double)gj_at(ab);  // gk_fkv_t.key is a float (estimate.c:437)
+            aty = (double)(float)GA::at(cab, j);  // G[j][ab]; gk_fkv_t.key is a float (estimate.c:437)
           }
           // in-block Gram rows: warp w stages rows 4w .. 4w+3
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             const int r = warp * 4 + u;
-            if (p0 + r < na) s_gbb[r][lane] = __ldg(Gab + (size_t)act[p0 + r] * kGramPW);
+            if (p0 + r < na) s_gbb[r][lane] = (Tile)GA::at(cab, act[p0 + r]);
           }
           // <a_m, yhat> for the 32 coordinates of the block: this warp's share of the sum over S
           const int len = sm.len;
-          sm.part[warp][lane] =
-              cache ? gram_gather_sum<GT, true>(Gab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW, sl_cpos,
-                                                cache + p0 + lane, npad)
-                    : gram_gather_sum<GT, false>(Gab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW);
+          sm.part[warp][lane] = gram_gather_sum<GA>(cab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW, s_stage[warp]);
           __syncthreads();
           if (warp == 0) {
             double ipf = 0.0;
@@ -405,65 +541,18 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
             const unsigned zerm = __ballot_sync(0xffffffffu, chg && myslot >= 0 && now == 0.0);
             const unsigned revm = __ballot_sync(0xffffffffu, chg && myslot >= 0 && was == 0.0);
             if (chg && myslot >= 0) sl_val[myslot] = now;
-            const int ncached0 = sm.ncached;
-            const int oldcp = (app && cache) ? cposp[pm] : -1;  // a coordinate that re-enters the list keeps its row
-            const unsigned needm = __ballot_sync(0xffffffffu, app && oldcp < 0);
             if (app) {
               const int pos = len + __popc(appm & ((1u << lane) - 1u));
-              const int want = ncached0 + __popc(needm & ((1u << lane) - 1u));
-              const int cp = oldcp >= 0 ? oldcp : (want < rows_cap ? want : -1);  // a cache row while there is room
               sl_row[pos] = ab;
               sl_val[pos] = now;
-              sl_cpos[pos] = cp;
-              cposp[pm] = cp;
               slotp[pm] = pos;
             }
             if (lane == 0) {
-              const int napp = __popc(appm);
-              sm.len = len + napp;
-              sm.napp = napp;
-              sm.ncached = min(rows_cap, ncached0 + __popc(needm));
+              sm.len = len + __popc(appm);
               sm.nzero += __popc(zerm) - __popc(revm);
             }
           }
           __syncthreads();
-          if (CS > 1 && cache != nullptr) {
-            // fill the cache rows handed out in this round: row k restricted to the active set, contiguous.
-            // The new entries are dealt over the CTAs of the cluster; a cluster barrier (release / acquire)
-            // publishes the rows before anyone's next gather reads them.  napp is identical in all CTAs.
-            const int napp = sm.napp;
-            if (napp > 0) {
-              const int first_e = sm.len - napp;
-              for (int i = 0; i < napp; i++) {
-                const int e = first_e + i;
-                const int cp = sl_cpos[e];
-                if (cp >= 0 && (uint32_t)(e % CS) == rank) {
-                  const int k = sl_row[e];
-                  GT *dst = cache + (size_t)cp * npad;
-                  // 8 independent gathers in flight per thread (a plain loop would serialise load -> store)
-                  for (int p0f = tid; p0f < (int)npad; p0f += NT * 8) {
-                    int it[8];
-                    GT v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                      const int p = p0f + u * NT;
-                      it[u] = p < na ? act[p] : -1;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; u++) v[u] = it[u] >= 0 ? __ldg(G + gram_off(nr, k, it[u])) : (GT)0;
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                      const int p = p0f + u * NT;
-                      if (p < (int)npad) __stcg(dst + p, v[u]);
-                    }
-                  }
-                }
-              }
-              __threadfence();
-              __syncthreads();
-              asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-            }
-          }
         }
         // ---- end of sweep: stop rule (cd.c:135-138)
         if (warp == 0) {
@@ -493,7 +582,7 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
         const int e = cb * 32 + lane;
         const int col = sl_row[e < len ? e : 0];
         const double vk = e < len ? sl_val[e] : 0.0;
-        const double s = gram_gather_sum<GT, false>(G + gram_off(nr, 0, col), sl_row, sl_val, len, warp, NW);
+        const double s = gram_gather_sum<GA>(GA::col(gv, col), sl_row, sl_val, len, warp, NW, s_stage[warp]);
         hh = fma(vk, s, hh);
       }
     }
@@ -513,7 +602,7 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
       for (int p = tid; p < na; p += NT) {
         const double xv = x[p];
         const double in = fabs(xv) > kEps ? xv : 0.0;
-        yd = fma(in, (double)gj_at(act[p]), yd);
+        yd = fma(in, gj_at(act[p]), yd);
         reg += 0.5 * a.l2r * xv * xv + a.l1r * fabs(xv);
         nnz_local += in != 0.0 ? 1 : 0;
       }

@@ -29,63 +29,21 @@ struct BatchArgs {
   size_t istride;    // >= ncols, multiple of 128 (whole panels of G)
   int32_t nwords;    // istride / 32
   int32_t profile;   // SLIMB200_PROFILE=1: thread 0 of rank 0 prints the cycle split of every batch
+  int32_t use_mma;   // the gather runs on the fp64 tensor-core path (DMMA m8n8k4) instead of scalar DFMAs
 };
 
-template <typename GT, int V>
-struct GVecLoad;
-template <>
-struct GVecLoad<float, 1> {
-  static __device__ __forceinline__ void ld(const float *p, float (&o)[1]) { o[0] = __ldg(p); }
-};
-template <>
-struct GVecLoad<float, 2> {
-  static __device__ __forceinline__ void ld(const float *p, float (&o)[2]) {
-    const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
-    o[0] = v.x;
-    o[1] = v.y;
-  }
-};
-template <>
-struct GVecLoad<float, 4> {
-  static __device__ __forceinline__ void ld(const float *p, float (&o)[4]) {
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
-    o[0] = v.x;
-    o[1] = v.y;
-    o[2] = v.z;
-    o[3] = v.w;
-  }
-};
-template <>
-struct GVecLoad<double, 1> {
-  static __device__ __forceinline__ void ld(const double *p, double (&o)[1]) { o[0] = __ldg(p); }
-};
-template <>
-struct GVecLoad<double, 2> {
-  static __device__ __forceinline__ void ld(const double *p, double (&o)[2]) {
-    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
-    o[0] = v.x;
-    o[1] = v.y;
-  }
-};
-template <>
-struct GVecLoad<double, 4> {
-  static __device__ __forceinline__ void ld(const double *p, double (&o)[4]) {
-    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
-    const double2 w = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-    o[0] = v.x;
-    o[1] = v.y;
-    o[2] = w.x;
-    o[3] = w.y;
-  }
-};
+// Row segments in the staging ring are kRingPad bytes apart from their natural stride so that the four entries a
+// DMMA B-fragment load touches (four consecutive ring rows, same 8 items) fall into different banks.
+constexpr int kRingPad = 32;
 
-template <typename GT, int CS, int T, int V, int NTB>
+template <typename GA, int CS, int T, int V, int NTB>
 struct __align__(16) BatchSmem {
+  using GT = typename GA::Tile;
   static constexpr int kBatchNW = NTB / 32;
   static constexpr int TV = T * V;
   static constexpr int OWN = CS > 1 ? TV / CS : 1;  // (target, v) pairs this CTA reduces
-  struct Ring {  // per-warp cp.async staging: row segments + entry values
-    GT g[kBatchStages * kBatchGroup][32][V];
+  struct Ring {  // per-warp cp.async staging: row segments (one panel row per entry, at most kMaxRowBytes) + entry values
+    unsigned char g[kBatchStages * kBatchGroup][GA::kMaxRowBytes + kRingPad];
     double v[kBatchStages * kBatchGroup][1][T];
   };
   union W {  // a warp's partial sums overwrite its OWN (drained) ring
@@ -108,13 +66,15 @@ struct __align__(16) BatchSmem {
 
 // add tagged peer store / wait from engine.cu: st_peer_tagged(), ld_tagged_wait()
 
-template <typename GT, int CS, int T, int V, int NTB>
+template <typename GA, int CS, int T, int V, int NTB, bool MMA>
 __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(const SolveArgs a, const GramArgs ga,
                                                                                const BatchArgs ba) {
   constexpr int NT = NTB, NW = NTB / 32, TV = T * V, BW = 32 * V;  // BW = items per block
   static_assert(T <= NW, "one chain warp per target");
   static_assert(CS == 1 || (TV % CS == 0 && TV / CS <= NW && CS <= TV), "exchange layout");
-  using Smem = BatchSmem<GT, CS, T, V, NTB>;
+  static_assert(V == 2, "a lane owns two adjacent items of the 64-item panel");
+  using Smem = BatchSmem<GA, CS, T, V, NTB>;
+  using GT = typename GA::Tile;
   extern __shared__ __align__(16) unsigned char batch_smem_raw[];
   Smem &sm = *reinterpret_cast<Smem *>(batch_smem_raw);
 
@@ -123,8 +83,7 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
   uint32_t tag = 0;
   int par = 0;
 
-  const GT *__restrict__ G = static_cast<const GT *>(ga.G);
-  const size_t nr = ga.nr;
+  const GramView &gv = ga.gv;
   static_assert(32 * V == kGramPW, "a block of coordinates is one panel of G");
   const size_t istride = ba.istride;
   const int nwords = ba.nwords;
@@ -207,7 +166,7 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
       }
       for (int base = 0; base < (int)istride; base += NT) {
         const int i = base + tid;  // istride is a multiple of 128: all warps stay in range
-        const bool f = i < a.ncols && i != j && (double)__ldg(G + gram_off(nr, j, i)) > a.l1r;
+        const bool f = i < a.ncols && i != j && GA::at(gv, j, i) > a.l1r;
         const uint32_t m = __ballot_sync(0xffffffffu, f);
         if (lane == 0 && i < (int)istride) amask[(size_t)t * nwords + (i >> 5)] = m;
         if (f) {
@@ -223,7 +182,7 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
           const int r = a.wcolind[k];
           if (r >= 0 && r < a.ncols) {
             const int i = a.rank[r];
-            if (i != j && (double)__ldg(G + gram_off(nr, j, i)) > a.l1r) xt[(size_t)t * istride + i] = (double)a.wcolval[k];
+            if (i != j && GA::at(gv, j, i) > a.l1r) xt[(size_t)t * istride + i] = (double)a.wcolval[k];
           }
         }
       }
@@ -278,16 +237,18 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
     pt = now_;                              \
   }
 
-    auto gather = [&](int b, double (&acc)[T][V]) {
-      // this warp's share of  sum_{e < len} val[e][t] * G[row[e]][block b]  for the lane's V items.
-      // The row segments (32*V elements, one per entry) and the T values of each entry are streamed
-      // through a per-warp shared-memory ring with cp.async (LDGSTS): kBatchStages groups of
-      // kBatchGroup entries, all but one in flight while one is consumed.  A lane reads back exactly
-      // the bytes it copied, so only the values need a warp-level hand-over.
+    // this warp's share of  sum_{e < len} val[e][t] * G[row[e]][block b]  for the lane's V items.
+    // The row segments (one 64-item panel row per entry: 64 x W bytes, W = element width of the panel) and the T
+    // values of each entry are streamed through a per-warp shared-memory ring with cp.async (LDGSTS): kBatchStages
+    // groups of kBatchGroup entries, all but one in flight while one is consumed.
+    auto gather_w = [&](int b, double (&acc)[T][V], auto wtag) {
+      constexpr int W = decltype(wtag)::value;                           // bytes per element: 1, 2, 4 (packed) or 8 (fp64)
       constexpr int GS = kBatchGroup, NG = kBatchStages, GPC = 32 / GS;  // GPC groups per 32-entry chunk
-      constexpr int LB = V * (int)sizeof(GT);                           // bytes per lane and entry
-      static_assert(LB == 8 || LB == 16, "cp.async element size");
-      const GT *__restrict__ Gblk = G + gram_off(nr, 0, b * BW) + (size_t)lane * V;  // panel b, row r at + r * PW
+      constexpr int RB = kGramPW * W;                                    // bytes of one panel row
+      constexpr int RS = RB + (W == 4 || W == 8 ? 32 : 16);              // ring stride of an entry (bank spreading)
+      static_assert(RS <= GA::kMaxRowBytes + kRingPad, "ring row");
+      constexpr int LB = RB / 32;                                        // bytes a lane consumes per entry
+      const unsigned char *const panel = GA::panel(gv, b * BW);           // row r of the panel at + r * RB
       const int len = sm.len;
       const int first = (int)rank * NW + warp, stride = CS * NW;
 #pragma unroll
@@ -298,22 +259,26 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
       const int nch = nchunk_all > first ? (nchunk_all - first + stride - 1) / stride : 0;  // my chunks
       const int ngr = nch * GPC;
       typename Smem::Ring &ring = sm.w[warp].ring;
-      const uint32_t g_base = smem_u32(&ring.g[0][0][0]) + (uint32_t)lane * LB;
-      const uint32_t v_base = smem_u32(&ring.v[0][0][0]) + (uint32_t)lane * 8u;
+      // copy layout: W >= 2: every lane copies the LB bytes it will consume; W == 1 (64-byte rows): lanes 0-15 copy
+      // one entry and lanes 16-31 the next one, 4 bytes each (cp.async moves at least 4 bytes)
+      constexpr int CB = LB < 4 ? 4 : LB;                    // bytes per lane and cp.async
+      constexpr int EPI = (32 * CB) / RB;                    // entries per cp.async instruction (1, or 2 for W == 1)
+      const int sub = EPI == 2 ? (lane >> 4) : 0;            // which of the EPI entries this lane copies
+      const uint32_t lane_off = EPI == 2 ? (uint32_t)(lane & 15) * CB : (uint32_t)lane * CB;
+      // dst: entries are RS apart; with two entries per instruction the upper half-warp writes the next entry
+      const uint32_t g_base = smem_u32(&ring.g[0][0]) + (EPI == 2 ? (uint32_t)sub * RS + (uint32_t)(lane & 15) * CB
+                                                                  : (uint32_t)lane * CB);
       int row_cur = 0, row_nxt = 0;
       if (nch > 0) {
         const int e = first * 32 + lane;
         row_nxt = e < len ? sl_row[e] : 0;
       }
-      // loop-invariant pieces of the addresses, kept in registers (the compiler otherwise rebuilds them per entry)
-      const char *const g_src0 = reinterpret_cast<const char *>(Gblk);
-      constexpr uint32_t kRowBytes = (uint32_t)(kGramPW * sizeof(GT));  // one row of the panel
-      constexpr uint32_t kSlotG = GS * 32 * LB, kSlotV = GS * T * 8;     // ring bytes per group
-      // `slot` is a compile-time constant at every call site (the main loop is unrolled over the ring),
-      // so all shared-memory addresses are base + immediate.  Per entry: one shuffle (row id), one
-      // mad.wide (row * row bytes + panel base) and one LDGSTS; the 8 x T values of a whole group are
-      // contiguous in the list (512 B) and travel with ONE 16-byte cp.async per lane.
-      unsigned long long g_src_u64 = reinterpret_cast<unsigned long long>(g_src0);
+      constexpr uint32_t kSlotG = GS * RS, kSlotV = GS * T * 8;  // ring bytes per group
+      // `slot` is a compile-time constant at every call site (the main loop is unrolled over the ring), so all
+      // shared-memory addresses are base + immediate.  Per copy: one shuffle (row id), one mad.wide (row * row
+      // bytes + panel base) and one LDGSTS; the 8 x T values of a whole group are contiguous in the list (512 B) and
+      // travel with ONE 16-byte cp.async per lane.
+      unsigned long long g_src_u64 = reinterpret_cast<unsigned long long>(panel) + lane_off;
       asm volatile("" : "+l"(g_src_u64));  // keep the panel base in registers (do not rebuild it per entry)
       static_assert(GS * T * 8 == 32 * 16, "one 16-byte cp.async per lane moves the values of a group");
       const char *const v_grp0 = reinterpret_cast<const char *>(slv) + (size_t)lane * 16;
@@ -332,29 +297,78 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
                        "l"(v_grp0 + (size_t)(c * 32 + i0) * (T * 8))
                        : "memory");
 #pragma unroll
-          for (int u = 0; u < GS; u++) {
-            const uint32_t r = (uint32_t)__shfl_sync(0xffffffffu, row_cur, i0 + u);
+          for (int u = 0; u < GS; u += EPI) {
+            const uint32_t r = (uint32_t)__shfl_sync(0xffffffffu, row_cur, i0 + u + sub);
             unsigned long long src;
-            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(src) : "r"(r), "r"(kRowBytes), "l"(g_src_u64));
-            if (LB == 8)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(gd + (uint32_t)(u * 32 * LB)), "l"(src) : "memory");
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(src) : "r"(r), "r"((uint32_t)RB), "l"(g_src_u64));
+            const uint32_t dst = gd + (uint32_t)(u * RS);
+            if (CB == 4)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+            else if (CB == 8)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
             else
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gd + (uint32_t)(u * 32 * LB)), "l"(src) : "memory");
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      const GT *const ring_g = &ring.g[0][lane][0];  // this lane's V elements of ring entry 0
+      const unsigned char *const ring_g = &ring.g[0][0] + lane * LB;  // this lane's V elements of ring entry 0
       const double *const ring_v = &ring.v[0][0][0];
       auto consume_entry = [&](const int se) {  // se: compile-time ring entry
-        GT gv[V];
-#pragma unroll
-        for (int v = 0; v < V; v++) gv[v] = ring_g[se * 32 * V + v];
+        double gd2[V];
+        if (W == 8) {
+          const double2 q = *reinterpret_cast<const double2 *>(ring_g + se * RS);
+          gd2[0] = q.x;
+          gd2[1] = q.y;
+        } else if (W == 4) {
+          const uint2 q = *reinterpret_cast<const uint2 *>(ring_g + se * RS);
+          gd2[0] = (double)q.x;
+          gd2[1] = (double)q.y;
+        } else if (W == 2) {
+          const uint32_t q = *reinterpret_cast<const uint32_t *>(ring_g + se * RS);
+          gd2[0] = (double)(q & 0xffffu);
+          gd2[1] = (double)(q >> 16);
+        } else {
+          const uint32_t q = (uint32_t)*reinterpret_cast<const unsigned short *>(ring_g + se * RS);
+          gd2[0] = (double)(q & 0xffu);
+          gd2[1] = (double)(q >> 8);
+        }
 #pragma unroll
         for (int t = 0; t < T; t++) {
           const double val = ring_v[se * T + t];
 #pragma unroll
-          for (int v = 0; v < V; v++) acc[t][v] = fma(val, (double)gv[v], acc[t][v]);
+          for (int v = 0; v < V; v++) acc[t][v] = fma(val, gd2[v], acc[t][v]);
+        }
+      };
+      // Tensor-core form of the same sums: one DMMA m8n8k4 multiplies the 8 x 4 block val[target][entry] (A, one
+      // double per lane: target = lane / 4, entry = lane % 4) with the 4 x 8 block G[entry][item] (B, one element per
+      // lane: entry = lane % 4, item = 8 n + lane / 4) and accumulates the 8 x 8 block of partial sums (two doubles
+      // per lane: target = lane / 4, items 8 n + 2 (lane % 4) + {0, 1}).  A block of 64 items is eight such column
+      // tiles; four ring entries are one k-step.  Same products and the same fp64 accumulation as the scalar form,
+      // 1/8 of the issue slots.
+      static_assert(!MMA || (T == 8 && V == 2), "DMMA tiling: 8 targets x 64 items");
+      double dm[8][2];
+      if (MMA) {
+#pragma unroll
+        for (int n = 0; n < 8; n++) dm[n][0] = dm[n][1] = 0.0;
+      }
+      const int kq = lane & 3, cq = lane >> 2;
+      const unsigned char *const ring_b = &ring.g[0][0] + kq * RS + cq * W;  // B fragment of ring entry 0, tile 0
+      const double *const ring_a = &ring.v[0][0][0] + kq * T + cq;           // A fragment of ring entry 0
+      auto consume_kstep = [&](const int se0, const bool valid) {  // se0: compile-time first ring entry of the k-step
+        const double av = valid ? ring_a[se0 * T] : 0.0;
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+          double bv;
+          const unsigned char *src = ring_b + se0 * RS + n * 8 * W;
+          if (W == 8) bv = *reinterpret_cast<const double *>(src);
+          else if (W == 4) bv = (double)*reinterpret_cast<const uint32_t *>(src);
+          else if (W == 2) bv = (double)*reinterpret_cast<const unsigned short *>(src);
+          else bv = (double)*src;
+          if (!valid) bv = 0.0;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(dm[n][0]), "+d"(dm[n][1])
+                       : "d"(av), "d"(bv));
         }
       };
 #pragma unroll
@@ -368,7 +382,16 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
             issue(g + NG - 1, (sidx + NG - 1) % NG);
             asm volatile("cp.async.wait_group %0;" ::"n"(NG - 1) : "memory");
             __syncwarp();
-            if (e0 + GS <= len) {  // whole group valid (warp-uniform): no per-entry tests
+            if (MMA) {
+              if (e0 + GS <= len) {  // whole group valid (warp-uniform)
+#pragma unroll
+                for (int u = 0; u < GS; u += 4) consume_kstep(sidx * GS + u, true);
+              } else {
+#pragma unroll
+                for (int u = 0; u < GS; u += 4)
+                  if (e0 + u < len) consume_kstep(sidx * GS + u, e0 + u + kq < len);
+              }
+            } else if (e0 + GS <= len) {  // whole group valid (warp-uniform): no per-entry tests
 #pragma unroll
               for (int u = 0; u < GS; u++) consume_entry(sidx * GS + u);
             } else {
@@ -384,6 +407,36 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
+      if (MMA) {
+        // hand the tile fragments over in the layout the rest of the kernel expects: acc[t][v] of lane L is the sum
+        // for target t and item 2 L + v.  This lane holds target cq, items 8 n + 2 kq + {0, 1} = 2 (4 n + kq) + v.
+        // The exchange goes through the warp's own (drained) ring.
+        double *xb = reinterpret_cast<double *>(&ring.g[0][0]);  // [T][32][V] doubles = 4 KB
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+          xb[(cq * 32 + 4 * n + kq) * V + 0] = dm[n][0];
+          xb[(cq * 32 + 4 * n + kq) * V + 1] = dm[n][1];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+          const double2 q = *reinterpret_cast<const double2 *>(xb + (t * 32 + lane) * V);
+          acc[t][0] = q.x;
+          acc[t][1] = q.y;
+        }
+        __syncwarp();
+      }
+    };
+    auto gather = [&](int b, double (&acc)[T][V]) {
+      if constexpr (GA::kMaxRowBytes == kGramPW * 8) {
+        gather_w(b, acc, std::integral_constant<int, 8>());
+      } else {
+        const int rb = GA::row_bytes(gv, b * BW);  // uniform over the block: the ranges are whole panels
+        if (rb == kGramPW * 4) gather_w(b, acc, std::integral_constant<int, 4>());
+        else if (rb == kGramPW * 2) gather_w(b, acc, std::integral_constant<int, 2>());
+        else gather_w(b, acc, std::integral_constant<int, 1>());
+      }
     };
 
     // ---- the sweeps (cd.c:112-140) -------------------------------------------------------------
@@ -417,8 +470,8 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
           act[v] = false;
         }
         if (mine_live) {
-          GT gj[V];
-          GVecLoad<GT, V>::ld(G + gram_off(nr, myj, item0), gj);
+          double gj[V];
+          GA::at2(gv, myj, item0, gj);
 #pragma unroll
           for (int v = 0; v < V; v++) {
             const int i = item0 + v;
@@ -428,18 +481,18 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
               den[v] = cn * cn + a.l2r;
               sq[v] = __ldg(a.csq + i);
             }
-            aty[v] = (double)(float)(double)gj[v];  // gk_fkv_t.key is a float (estimate.c:437)
+            aty[v] = (double)(float)gj[v];  // gk_fkv_t.key is a float (estimate.c:437)
             xv[v] = xt[(size_t)warp * istride + i];
           }
         }
         // in-block Gram rows (shared by the T chains): warp w stages rows w, w+NW, ...
         for (int r = warp; r < BW; r += NW) {
-          GT row[V];
+          double row[V];
 #pragma unroll
-          for (int v = 0; v < V; v++) row[v] = (GT)0;
-          if (b * BW + r < a.ncols) GVecLoad<GT, V>::ld(G + gram_off(nr, b * BW + r, item0), row);
+          for (int v = 0; v < V; v++) row[v] = 0.0;
+          if (b * BW + r < a.ncols) GA::at2(gv, b * BW + r, item0, row);
 #pragma unroll
-          for (int v = 0; v < V; v++) sm.gbb[r][lane * V + v] = row[v];
+          for (int v = 0; v < V; v++) sm.gbb[r][lane * V + v] = (GT)row[v];
         }
         double acc[T][V];
         if (ba.profile && tid == 0) pt = clock64();
@@ -672,7 +725,7 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
           const double xv = x[i];
           if (xv != 0.0) {
             const double in = fabs(xv) > kEps ? xv : 0.0;
-            yd = fma(in, (double)__ldg(G + gram_off(nr, j, i)), yd);
+            yd = fma(in, GA::at(gv, j, i), yd);
             reg += 0.5 * a.l2r * xv * xv + a.l1r * fabs(xv);
             nnz_local += in != 0.0 ? 1 : 0;
           }

@@ -60,10 +60,14 @@ def model_views(handle):
     return out
 
 
-def options(l1r=1.0, l2r=1.0, opttol=None, niters=None, nthreads=None, dbglvl=0):
+def options(l1r=1.0, l2r=1.0, opttol=None, niters=None, nthreads=None, dbglvl=0, nnbrs=None, simtype=None):
     io = np.full(NOPTIONS, -1, dtype=np.int32)
     do = np.full(NOPTIONS, -1.0, dtype=np.float64)
     io[OPT_DBGLVL] = dbglvl
+    if nnbrs is not None:
+        io[OPT_NNBRS] = nnbrs
+    if simtype is not None:
+        io[OPT_SIMTYPE] = SIMTYPES[simtype]
     if nthreads is not None:
         io[OPT_NTHREADS] = nthreads
     if niters is not None:
@@ -144,6 +148,69 @@ class SlimLib:
         return ids, sc
 
 
+def capture_stdout(fn):
+    """Run fn() with the process-level stdout (C printf included) redirected; returns (result, text)."""
+    import sys
+    import tempfile
+
+    sys.stdout.flush()
+    libc = C.CDLL("libc.so.6")
+    libc.fflush(None)
+    saved = os.dup(1)
+    with tempfile.TemporaryFile("w+b") as tf:
+        os.dup2(tf.fileno(), 1)
+        try:
+            out = fn()
+        finally:
+            libc.fflush(None)
+            os.dup2(saved, 1)
+            os.close(saved)
+        tf.seek(0)
+        return out, tf.read().decode(errors="replace")
+
+
+def mselect(lib, trn, tst, l1s, l2s, nrcmds=10, **opt):
+    """Py_SLIM_Mselect of a libslim.so-compatible library (reference pyapi.c:214-412) on CSR triples.
+    Returns (rc, best[8] = l1HR, l2HR, HRHR, ARHR, l1AR, l2AR, HRAR, ARAR, per-cell rows parsed from the
+    library's own printout: l1r, l2r, nnz, hr, hr_head, hr_tail, arhr)."""
+    import re
+
+    L = lib.lib
+    L.Py_csr_wrapper.restype = C.c_int32
+    L.Py_csr_wrapper.argtypes = [C.c_int32, C.POINTER(C.c_ssize_t), C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                 C.POINTER(C.c_void_p)]
+    L.Py_csr_free.argtypes = [C.c_void_p]
+    L.Py_SLIM_Mselect.restype = C.c_int32
+    L.Py_SLIM_Mselect.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.c_int32] + \
+        [C.POINTER(C.c_double)] * 8
+    hs = []
+    keep = []
+    for rp, ri, rv in (trn, tst):
+        rp = np.ascontiguousarray(rp, np.int64)
+        ri = np.ascontiguousarray(ri, np.int32)
+        rv = np.ascontiguousarray(rv, np.float32)
+        keep.append((rp, ri, rv))
+        h = C.c_void_p()
+        assert L.Py_csr_wrapper(len(rp) - 1, _p(rp, C.c_ssize_t), _p(ri, C.c_int32), _p(rv, C.c_float),
+                                C.byref(h)) == SLIM_OK
+        hs.append(h)
+    io, do = options(**opt)
+    io[OPT_NRCMDS] = nrcmds
+    a1 = np.ascontiguousarray(l1s, np.float64)
+    a2 = np.ascontiguousarray(l2s, np.float64)
+    best = [C.c_double(0.0) for _ in range(8)]
+    rc, text = capture_stdout(lambda: L.Py_SLIM_Mselect(hs[0], hs[1], _p(io, C.c_int32), _p(do, C.c_double),
+                                                        _p(a1, C.c_double), _p(a2, C.c_double), len(a1), len(a2),
+                                                        *[C.byref(b) for b in best]))
+    for h in hs:
+        L.Py_csr_free(h)
+    pat = re.compile(r"l1r:\s*(\S+)\s+l2r:\s*(\S+)\s+nnz:\s*(\d+)\s+hr:\s*(\S+)\s+hr_head:\s*(\S+)\s+hr_tail:\s*(\S+)"
+                     r"\s+arhr:\s*(\S+)")
+    cells = np.array([[float(x) for x in m.groups()] for m in pat.finditer(text)], dtype=np.float64)
+    return rc, np.array([b.value for b in best]), cells
+
+
 # ----------------------------------------------------------------------------------------------
 # oracle/ loaders
 # ----------------------------------------------------------------------------------------------
@@ -172,13 +239,15 @@ def libc_srand(seed=1):
 
 class _OParams(C.Structure):
     _fields_ = [("l1r", C.c_double), ("l2r", C.c_double), ("optTol", C.c_double),
-                ("maxniters", C.c_int32), ("order", C.c_int32), ("nthreads", C.c_int32)]
+                ("maxniters", C.c_int32), ("order", C.c_int32), ("nthreads", C.c_int32),
+                ("nnbrs", C.c_int32), ("simtype", C.c_int32), ("nbr_ties", C.c_int32)]
 
 
 class _OCsc(C.Structure):
     _fields_ = [("nrows", C.c_int32), ("ncols", C.c_int32), ("colptr", C.POINTER(C.c_int64)),
                 ("colind", C.POINTER(C.c_int32)), ("colval", C.POINTER(C.c_float)),
-                ("cnorms", C.POINTER(C.c_float))]
+                ("cnorms", C.POINTER(C.c_float)), ("rowptr", C.POINTER(C.c_int64)),
+                ("rowind", C.POINTER(C.c_int32)), ("rowval", C.POINTER(C.c_float))]
 
 
 class _OStats(C.Structure):
@@ -188,6 +257,8 @@ class _OStats(C.Structure):
 
 
 ORDER_ASCENDING, ORDER_REF_RAND, ORDER_POPULARITY = 0, 1, 2
+TIES_REFERENCE, TIES_POPULARITY = 0, 1
+SIMTYPES = {"cos": 0, "jac": 1, "dotp": 2}
 
 
 class Oracle:
@@ -241,13 +312,14 @@ class Oracle:
         self.lib.oracle_free_csc(m)
 
     def learn(self, rowptr, rowind, rowval, l1r=1.0, l2r=1.0, opttol=1e-7, niters=10000,
-              order=ORDER_ASCENDING, nthreads=1, cols=None, imodel=None, want_stats=False):
+              order=ORDER_ASCENDING, nthreads=1, cols=None, imodel=None, want_stats=False,
+              nnbrs=0, simtype="cos", nbr_ties=TIES_REFERENCE):
         """Returns dict(colptr, colind, colval[, stats]) for the solved columns (in `cols` order).
         imodel: optional (ncols, colptr, colind, colval) CSC of a warm-start model."""
         m = self.setup(rowptr, rowind, rowval)
         try:
             ncols = m.contents.ncols
-            p = _OParams(l1r, l2r, opttol, niters, order, nthreads)
+            p = _OParams(l1r, l2r, opttol, niters, order, nthreads, nnbrs, SIMTYPES[simtype], nbr_ties)
             cs = None if cols is None else np.ascontiguousarray(cols, dtype=np.int32)
             nsel = ncols if cs is None else len(cs)
             st = None

@@ -271,22 +271,63 @@ def test_window_sweep_large_and_small_columns(lib, ours, oracle, monkeypatch):
 
 # ---- the Gram-space solver (slim_b200/csrc/gram.cuh): the default whenever G = R^T R fits in HBM ----------
 
-def test_gram_matrix_is_exact(lib):
-    # G staged by gram_build_kernel == R^T R in the engine's internal item order, bit for bit (integer ratings)
+@pytest.mark.parametrize("width", ["0", "2", "4"])
+def test_gram_matrix_is_exact(lib, monkeypatch, width):
+    # G staged by gram_build_kernel == R^T R in the engine's internal item order, bit for bit (integer ratings).
+    # The packed layout stores a column in 8, 16 or 32 bits depending on its bound rmax * csq_i (gram.cuh);
+    # width "0" is that natural layout, "2" forbids the 8-bit range, "4" stores everything in 32 bits.
     import scipy.sparse as sp
 
     from slim_b200 import Staged
 
-    for ratings in (False, True):
-        rp, ri, rv = st.synth_zipf(3000, 200, 25, seed=8, ratings=ratings)
-        R = sp.csr_matrix((rv.astype(np.float64), ri, rp), shape=(3000, 200))
+    monkeypatch.setenv("SLIMB200_GRAM_WIDTH", width)
+    for ratings, nu, ni, per in ((False, 3000, 200, 25), (True, 3000, 200, 25), (True, 9000, 1200, 12)):
+        rp, ri, rv = st.synth_zipf(nu, ni, per, seed=8, ratings=ratings)
+        R = sp.csr_matrix((rv.astype(np.float64), ri, rp), shape=(nu, ni))
         G = (R.T @ R).toarray()
         with Staged(rp, ri, rv) as s:
             got = s.gram()
             rank = s.item_order()
+            nbytes, h32, h16 = s.gram_layout()
         assert got is not None and got.dtype == np.float32
         inv = np.argsort(rank)
         assert np.array_equal(got.astype(np.float64), G[np.ix_(inv, inv)])
+        ld = (ni + 127) // 128 * 128
+        assert 0 <= h32 <= h16 <= ld and h32 % 64 == 0 and h16 % 64 == 0
+        assert nbytes == ni * (4 * h32 + 2 * (h16 - h32) + (ld - h16)) + 16
+        if width == "4":
+            assert h32 == ld
+        elif width == "2":
+            assert h16 == ld
+        else:  # the bound that picks a column's width: rmax * (sum of squares of the column)
+            csq = np.asarray(R.multiply(R).sum(axis=0)).ravel()[inv] * rv.max()
+            assert all(csq[i] <= 65535 for i in range(h32, ni)) and all(csq[i] <= 255 for i in range(h16, ni))
+            assert h32 == 0 or csq[h32 - 64:h32].max() > 65535  # ... and the ranges are as large as they can be
+            assert h16 == h32 or csq[h16 - 64:h16].max() > 255
+    if width == "0":
+        assert h32 > 0 and h16 > h32 and h16 < ld  # the last matrix has all three ranges
+
+
+@pytest.mark.parametrize("width", ["0", "2", "4"])
+@pytest.mark.parametrize("route", ["single", "cluster", "batch"])
+def test_gram_packed_widths_all_kernels(lib, oracle, monkeypatch, width, route):
+    # every Gram-space kernel reads the packed layout through the same accessors: all three element widths, per kernel
+    monkeypatch.setenv("SLIMB200_GRAM_WIDTH", width)
+    monkeypatch.setenv("SLIMB200_GRAM_CS", "4")
+    monkeypatch.setenv("SLIMB200_GRAM_HEAVY", "0" if route == "cluster" else "1000000000")
+    monkeypatch.setenv("SLIMB200_GRAM_BATCH", "0" if route == "batch" else "1000000000")
+    from slim_b200 import Staged, learn_columns
+
+    rp, ri, rv = st.synth_zipf(9000, 1200, 12, seed=8, ratings=True)  # 32-, 16- and 8-bit columns (see above)
+    cols = np.arange(0, 1200, 5, dtype=np.int32)
+    with Staged(rp, ri, rv) as s:
+        r = learn_columns(s, dict(niters=40), cols=cols)
+        got, stats = r.to_host(), r.stats()
+    ref = oracle.learn(rp, ri, rv, niters=40, cols=cols, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
+    assert np.array_equal(stats["nactive"], ref["stats"]["nactive"])
+    assert np.array_equal(stats["niters"], ref["stats"]["niters"])
+    _check_close(got, ref, tol=1e-6)
+    assert np.allclose(stats["objval"], ref["stats"]["objval"], rtol=1e-9)
 
 
 @pytest.mark.parametrize("cs", ["1", "2", "4", "8", "16"])
@@ -383,11 +424,8 @@ def test_gram_and_user_space_kernels_agree(lib, monkeypatch):
     assert np.allclose(out["1"][1]["objval"], out["0"][1]["objval"], rtol=1e-9)
 
 
-@pytest.mark.parametrize("cache_mb", ["0", "1", "1024"])
-def test_gram_row_cache(lib, ours, oracle, monkeypatch, cache_mb):
-    # the one-target clusters cache each nonzero coordinate's Gram row restricted to the active set: off, too
-    # small for all rows (1 MB per cluster: mixed cached / uncached entries) and large enough for everything
-    monkeypatch.setenv("SLIMB200_GRAM_CACHE_MB", cache_mb)
+def test_gram_medium_matrix_cluster_class(lib, oracle, monkeypatch):
+    # 2 000 items: element offsets beyond one panel range, 8-bit and 16-bit columns side by side in one block
     monkeypatch.setenv("SLIMB200_GRAM_HEAVY", "0")
     monkeypatch.setenv("SLIMB200_GRAM_BATCH", "1000000000")
     from slim_b200 import Staged, learn_columns
@@ -397,6 +435,8 @@ def test_gram_row_cache(lib, ours, oracle, monkeypatch, cache_mb):
     with Staged(rp, ri, rv) as s:
         r = learn_columns(s, dict(niters=50), cols=cols)
         got, stats = r.to_host(), r.stats()
+        _, h32, h16 = s.gram_layout()
+    assert h32 < h16 < 2048
     ref = oracle.learn(rp, ri, rv, niters=50, cols=cols, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
     assert np.array_equal(stats["niters"], ref["stats"]["niters"])
     _check_close(got, ref, tol=1e-6)
@@ -580,3 +620,94 @@ def test_model_selection_keeps_matrix_resident(lib, automotive, capfd):
     assert best["bestl1HR"] in (1.0, 5.0) and best["bestARAR"] > 0.04
     out = capfd.readouterr().out
     assert out.count("Using Coordinate Descent!") == 2 and "hr_head" in out
+
+
+# ---- fSLIM (nnbrs > 0): fslim.cuh + cd_gram_kernel; reference neighbors.c:16-125, estimate.c:424-431 ----------
+
+@pytest.mark.parametrize("name", ["ml100k", "automotive"])
+@pytest.mark.parametrize("sim", ["cos", "jac", "dotp"])
+def test_fslim_matches_reference_golden(lib, ours, name, sim):
+    # same neighbour SETS as the reference, boundary ties included (the kernel rebuilds the reference's candidate
+    # order and runs its selection), weights within the converged tolerance
+    g, f = st.load_golden(name), st.load_golden("fslim")
+    nn = int(f["nnbrs"])
+    io, do = st.options(l1r=1.0, l2r=1.0, nnbrs=nn, simtype=sim, **CONV)
+    h, status = ours.learn(g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], io, do)
+    assert h and status == st.SLIM_OK
+    mv = st.model_views(h)
+    ref = dict(colptr=f[f"{name}_{sim}_colptr"], colind=f[f"{name}_{sim}_colind"], colval=f[f"{name}_{sim}_colval"])
+    _check_close(mv, ref)
+    assert np.diff(mv["colptr"]).max() <= nn
+    ours.free(h)
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_fslim_default_setting_matches_oracle(lib, ours, oracle, binary):
+    # capped / default tolerance, same visiting order as the oracle: iterate-level agreement
+    rp, ri, rv = st.synth_zipf(6000, 500, 30, seed=5, ratings=not binary)
+    io, do = st.options(l1r=0.3, l2r=1.0, niters=50, nnbrs=25, simtype="cos")
+    h, status = ours.learn(rp, ri, None if binary else rv, io, do)
+    assert h and status == st.SLIM_OK
+    w = oracle.learn(rp, ri, None if binary else rv, l1r=0.3, l2r=1.0, niters=50, nthreads=8, nnbrs=25,
+                     simtype="cos", nbr_ties=st.TIES_REFERENCE, order=st.ORDER_POPULARITY)
+    _check_close(st.model_views(h), w, tol=1e-6)
+    ours.free(h)
+
+
+def test_ordered_flag_keeps_the_plain_slim_path(lib, ours):
+    # api.c:54-60 + estimate.c:396,424: `ordered` only relabels the model type; with nnbrs > 0 it even switches the
+    # neighbour restriction OFF (only SLIM_MTYPE_FSLIM is special-cased)
+    g = st.load_golden("automotive")
+    base = _learn(ours, g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], niters=50)
+    ref = st.model_views(base)
+    for nnbrs in (0, 10):
+        io, do = st.options(l1r=1.0, l2r=1.0, niters=50, nnbrs=nnbrs)
+        io[st.OPT_ORDERED] = 1
+        h, status = ours.learn(g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], io, do)
+        assert h and status == st.SLIM_OK
+        mv = st.model_views(h)
+        assert np.array_equal(mv["colind"], ref["colind"]) and np.array_equal(mv["colval"], ref["colval"])
+        ours.free(h)
+    ours.free(base)
+
+
+# ---- model selection pinned to the reference (pyapi.c:214-412) -----------------------------------------------
+
+def test_mselect_matches_reference_golden(lib, ours):
+    g, ms = st.load_golden("automotive"), st.load_golden("mselect")
+    trn = (g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"])
+    tst = (g["tst_rowptr"], g["tst_rowind"], g["tst_rowval"])
+    rc, best, cells = st.mselect(ours, trn, tst, ms["l1"], ms["l2"], nrcmds=10, **CONV)
+    assert rc == st.SLIM_OK
+    assert cells.shape == ms["cells"].shape
+    assert np.array_equal(cells[:, :2], ms["cells"][:, :2])                       # the (l1, l2) of every cell
+    assert np.abs(cells[:, 2] - ms["cells"][:, 2]).max() <= 2                     # nnz(W): support flips below 2e-6
+    assert np.array_equal(cells[:, 3:], ms["cells"][:, 3:]), (cells, ms["cells"])  # HR / head / tail / ARHR, 4 dp
+    assert np.array_equal(best[[0, 1, 4, 5]], ms["best"][[0, 1, 4, 5]])           # the chosen (l1, l2) pairs
+    assert np.allclose(best[[2, 3, 6, 7]], ms["best"][[2, 3, 6, 7]], rtol=0, atol=5e-5)
+
+
+def test_automotive_gpu_topn_matches_golden_lists(lib, ours):
+    # batched GPU top-N (predict.cuh) on the second fixture against the reference's own lists
+    g = st.load_golden("automotive")
+    h = _learn(ours, g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], **CONV)
+    from slim_b200 import _lib as L_
+
+    L = L_.load()
+    mats = []
+    for rp, ri, rv in ((g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"]),):
+        rp, ri, rv = (np.ascontiguousarray(rp, np.int64), np.ascontiguousarray(ri, np.int32),
+                      np.ascontiguousarray(rv, np.float32))
+        hm = C.c_void_p()
+        assert L.Py_csr_wrapper(len(rp) - 1, rp.ctypes.data_as(C.POINTER(C.c_ssize_t)),
+                                ri.ctypes.data_as(C.POINTER(C.c_int32)), rv.ctypes.data_as(C.POINTER(C.c_float)),
+                                C.byref(hm)) == st.SLIM_OK
+        mats.append((hm, rp, ri, rv))
+    nu = len(g["trn_rowptr"]) - 1
+    ids = np.full((nu, 10), -1, np.int32)
+    sc = np.zeros((nu, 10), np.float32)
+    assert L.Py_SLIM_Predict(10, h, mats[0][0], ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                             sc.ctypes.data_as(C.POINTER(C.c_float))) == st.SLIM_OK
+    assert np.array_equal(ids, g["top10_ids"])
+    L.Py_csr_free(mats[0][0])
+    ours.free(h)
