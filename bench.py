@@ -60,8 +60,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SLIM_BENCH_WORKLOAD", "c4"))
-    ap.add_argument("--cols-per-step", type=int, default=int(os.environ.get("SLIM_BENCH_COLS", "12288")),
-                    help="target columns per step PER GPU")
+    ap.add_argument("--cols-per-step", type=int, default=int(os.environ.get("SLIM_BENCH_COLS", "0")),
+                    help="target columns per step PER GPU (0: 12288; 256 for c5, whose Gram matrix does not fit in "
+                         "HBM so that every target streams R)")
     ap.add_argument("--cpu-cols", type=int, default=int(os.environ.get("SLIM_BENCH_CPU_COLS", "0")),
                     help="columns per reference step (0: four per host thread)")
     ap.add_argument("--l1r", type=float, default=1.0)
@@ -218,6 +219,46 @@ def host_objective(rp, ri, rv, cols, w, l1r, l2r):
     return out
 
 
+def slim_learn_entry_point(nthreads):
+    """The real entry point, timed end to end: SLIM_Learn (all columns, host CSR in, malloc'd model with both views
+    out -- staging, Gram build, solve, GPU-built CSR index and the copies included) on the SURVEY.md probe matrix
+    (20 000 x 2 000, 1 M nnz, niters 50), next to the reference's SLIM_Learn on all host cores."""
+    import slimtest as st
+    from slim_b200 import _lib
+    from slim_b200.synth import zipf_csr
+
+    rp, ri, rv = (t.numpy() for t in zipf_csr(20_000, 2_000, 50))
+    out = {"workload": "SLIM_Learn, all 2000 columns of a 20000 x 2000 / 1M nnz Zipf(1.1) matrix, niters=50"}
+    io, do = st.options(l1r=1.0, l2r=1.0, opttol=PARAMS["optTol"], niters=PARAMS["niters"], nthreads=nthreads)
+    old = os.environ.get("SLIMB200_GPUS")
+    os.environ["SLIMB200_GPUS"] = "1"
+    try:
+        ours = st.SlimLib(_lib.LIB_PATH)
+        for rep in range(2):  # first call pays the CUDA context / module load
+            t0 = time.perf_counter()
+            (h, status), _ = _capture_stdout(lambda: ours.learn(rp, ri, rv, io, do))
+            dt = time.perf_counter() - t0
+            assert h and status == st.SLIM_OK
+            nnz = int(st.model_views(h)["colptr"][-1])
+            ours.free(h)
+        out.update(ours_s=round(dt, 4), ours_nnz=nnz, ours_columns_per_s=round(2000 / dt, 1))
+    finally:
+        if old is None:
+            os.environ.pop("SLIMB200_GPUS", None)
+        else:
+            os.environ["SLIMB200_GPUS"] = old
+    if st.ref_lib_path().exists():
+        ref = st.load_ref()
+        t0 = time.perf_counter()
+        (h, status), _ = _capture_stdout(lambda: ref.learn(rp, ri, rv, io, do))
+        dt = time.perf_counter() - t0
+        nnz = int(st.model_views(h)["colptr"][-1])
+        ref.free(h)
+        out.update(reference_s=round(dt, 3), reference_nnz=nnz, reference_threads=nthreads,
+                   reference_columns_per_s=round(2000 / dt, 1))
+    return out
+
+
 def run_reference(args, rp, ri, rv, colcnt, steps, warmup, keep_w=None):
     import slimtest as st
 
@@ -243,6 +284,8 @@ def run_reference(args, rp, ri, rv, colcnt, steps, warmup, keep_w=None):
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    if args.cols_per_step <= 0:
+        args.cols_per_step = 256 if args.workload == "c5" else 12288
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -459,6 +502,13 @@ def main():
             cpu_baseline = {"value": None, "unit": "columns/s", "cores": os.cpu_count(), "kind": "reference",
                             "sample": f"failed: {ex!r}"}
 
+    entry_point = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            entry_point = slim_learn_entry_point(os.cpu_count() or 1)
+        except Exception as ex:
+            entry_point = {"failed": repr(ex)}
+
     if rank == 0:
         line = dict(base, value=value, ms_per_step=1e3 * wall / args.steps,
                     config={"workload": wl_name, "cols_per_step_per_gpu": args.cols_per_step,
@@ -473,7 +523,8 @@ def main():
                                                 % (gram_h32, gram_h32, gram_h16)) if gram_eb == 4 else
                                                ("fp64" if gram_eb == 8 else "not staged"),
                                      "build_ms": round(gram_ms, 1), "GB": round(gram_bytes / 1e9, 2)}},
-                    roofline=roofline, cpu_baseline=cpu_baseline, parity_check=parity_check, e2e=e2e, clocks=clocks,
+                    roofline=roofline, cpu_baseline=cpu_baseline, parity_check=parity_check, e2e=e2e,
+                    slim_learn_entry_point=entry_point, clocks=clocks,
                     gpu_launches=int(launches))
         print(json.dumps(line))
     staged.close()

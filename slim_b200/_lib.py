@@ -74,10 +74,30 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 _lib = None
 
 
+def _prefer_bundled_nccl():
+    """libslim.so binds NCCL at run time (dlopen "libnccl.so.2").  In a python environment that also holds torch,
+    point it at the NCCL wheel torch itself loads (site-packages/nvidia/nccl/lib/libnccl.so.2), so that the two
+    never end up with different NCCL builds under one soname -- whichever of them is imported first."""
+    if os.environ.get("SLIMB200_NCCL_LIBRARY"):
+        return
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = Path(base) / "lib" / "libnccl.so.2"
+            if cand.exists():
+                os.environ["SLIMB200_NCCL_LIBRARY"] = str(cand)
+                return
+    except Exception:
+        pass
+
+
 def load():
     """Load libslim.so (once) and attach the argument types of every exported entry point."""
     global _lib
     if _lib is None:
+        _prefer_bundled_nccl()
         if not LIB_PATH.exists():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -m slim_b200.build` "

@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1441,28 +1442,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// Remote (DSMEM) 8-byte store that signals an mbarrier in the DESTINATION CTA: the exchange of the
-// per-CTA partial inner products needs no cluster-wide barrier, each CTA just waits on its own mbarrier.
-__device__ __forceinline__ void st_async_peer(void *local_dst, unsigned long long *local_bar, uint32_t peer_rank,
-                                              double v) {
-  uint32_t rdst, rbar;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(local_dst)), "r"(peer_rank));
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar)), "r"(peer_rank));
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(rdst),
-               "l"(__double_as_longlong(v)), "r"(rbar)
-               : "memory");
-}
-// Bulk copy from this CTA's shared memory into a peer CTA's shared memory, completion (bytes) counted
-// on the PEER's mbarrier: one message and one barrier update per destination.
-__device__ __forceinline__ void bulk_s2peer(void *local_dst, const void *local_src, uint32_t bytes,
-                                            unsigned long long *local_bar, uint32_t peer_rank) {
-  uint32_t rdst, rbar;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(local_dst)), "r"(peer_rank));
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar)), "r"(peer_rank));
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rdst),
-               "r"(smem_u32(local_src)), "r"(bytes), "r"(rbar)
-               : "memory");
-}
 // Flag-in-data exchange (the "LL" idea of NCCL): every 8-byte remote store carries 4 bytes of payload
 // and a 4-byte round tag; 8-byte stores are single-copy atomic, so the receiver simply polls its OWN
 // shared memory until all tags match -- no fence, no barrier, no mbarrier on the critical path.
@@ -1482,27 +1461,6 @@ __device__ __forceinline__ double ld_tagged_wait(const unsigned long long *src, 
     asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(addr) : "memory");
   } while ((uint32_t)(w0 >> 32) != tag || (uint32_t)(w1 >> 32) != tag);
   return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-}
-// (kept for reference) generic-proxy exchange with a release-arrive on the PEER's mbarrier
-__device__ __forceinline__ void st_peer_f64(double *local_dst, uint32_t peer_rank, double v) {
-  uint32_t rdst;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(local_dst)), "r"(peer_rank));
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(rdst), "d"(v) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_peer(unsigned long long *local_bar, uint32_t peer_rank) {
-  uint32_t rbar;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar)), "r"(peer_rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(unsigned long long *bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -2829,9 +2787,9 @@ static int cluster_dispatch(bool vals, bool window, const SolveArgs &args, const
 
 // Launch (or, with query_only, size) cd_gram_kernel<GT, CS>.  Query: CTAs per SM for CS == 1, co-resident
 // clusters on the device for CS > 1.  `count` = CTAs (CS == 1) or clusters (CS > 1) to launch.
-template <typename GA, int CS>
+template <typename GA, int CS, int UNR>
 static int gram_launch_t(const SolveArgs &args, const GramArgs &gargs, int count, cudaStream_t s, bool query_only) {
-  auto kern = cd_gram_kernel<GA, CS>;
+  auto kern = cd_gram_kernel<GA, CS, UNR>;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -2857,10 +2815,16 @@ static int gram_launch_t(const SolveArgs &args, const GramArgs &gargs, int count
 
 static int gram_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &gargs, int count, cudaStream_t s,
                        bool query_only) {
+  // the deep-unroll variant exists for the packed layout and the two default shapes (single CTA, clusters of 4)
+  const bool deep = !f64 && (cs == 1 || cs == 4) && env_int("SLIMB200_GRAM_UNROLL", 32) == 32;
+  if (deep) {
+    return cs == 1 ? gram_launch_t<GaPacked, 1, 32>(args, gargs, count, s, query_only)
+                   : gram_launch_t<GaPacked, 4, 32>(args, gargs, count, s, query_only);
+  }
 #define SLIM_GRAM_CS(CSV)                                                                        \
   if (cs == CSV)                                                                                 \
-    return f64 ? gram_launch_t<GaF64, CSV>(args, gargs, count, s, query_only)                    \
-               : gram_launch_t<GaPacked, CSV>(args, gargs, count, s, query_only);
+    return f64 ? gram_launch_t<GaF64, CSV, 16>(args, gargs, count, s, query_only)                \
+               : gram_launch_t<GaPacked, CSV, 16>(args, gargs, count, s, query_only);
   SLIM_GRAM_CS(1)
   SLIM_GRAM_CS(2)
   SLIM_GRAM_CS(4)
@@ -2935,6 +2899,10 @@ static int env_int(const char *name, int dflt) {
 Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel_in,
               const WarmStart *warm, int32_t *status) {
   Result *res = nullptr;
+  // SLIMB200_VERBOSE=2: host wall-clock split of the call (plan + scratch, solve, gather, release)
+  auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double w_start = wall();
+  double w_plan = 0, w_solved = 0, w_gathered = 0;
   try {
     DeviceGuard guard(m->device);
     (void)cudaGetLastError();
@@ -3057,15 +3025,13 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       if (gram_cs != 1 && gram_cs != 2 && gram_cs != 4 && gram_cs != 8 && gram_cs != 16) gram_cs = 4;
       // fSLIM targets have at most nnbrs active coordinates: one CTA each
       const int gram_heavy = fslim ? INT32_MAX : env_int("SLIMB200_GRAM_HEAVY", 2000);
-      // measured on C4 (profiles/r01_gram_class_routing.txt): below ~30K nonzeros a batch of 8 targets costs more
-      // SM-seconds than eight one-target clusters (the union nonzero list is much longer than each target's own and
-      // the item-space blocks cover inactive coordinates), so by default the two batch classes coincide
-      const int gram_batch = fslim ? INT32_MAX : std::max(gram_heavy, env_int("SLIMB200_GRAM_BATCH", 30000));
-      const int gram_top = fslim ? INT32_MAX : std::max(gram_batch, env_int("SLIMB200_GRAM_TOP", 30000));
-      int32_t ntop = 0;
-      for (int32_t q = 0; q < nsel; q++)
-        if (m->h_colcnt[m->h_rank[colof(q)]] >= gram_top) ntop++;
-      const bool few_top = (ntop + kBatchT - 1) / kBatchT <= 2 * std::max(1, m->sm_count / 16);
+      // measured on C4 (profiles/r02_plan_sweeps.txt): with the packed Gram matrix and the DMMA gather a batch of 8
+      // targets beats eight one-target clusters from ~9 000 nonzeros on (30 000 in round 1: scalar DFMAs, fp32 G);
+      // the one-target clusters are bound by the DRAM's random-sector rate, the batches read whole panel rows and
+      // share them between their targets.  16 CTAs x 512 threads per batch is the best shape at every batch count
+      // (8 x 256 with two CTAs per SM was measured 15-45 % slower); the second batch class stays for experiments.
+      const int gram_batch = fslim ? INT32_MAX : std::max(gram_heavy, env_int("SLIMB200_GRAM_BATCH", 9000));
+      const int gram_top = fslim ? INT32_MAX : std::max(gram_batch, env_int("SLIMB200_GRAM_TOP", 9000));
       auto batch_cs_of = [&](int dflt) {
         const int v = env_int("SLIMB200_BATCH_CS", dflt);
         return (v == 1 || v == 4 || v == 8 || v == 16) ? v : dflt;
@@ -3073,7 +3039,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       auto batch_nt_of = [&](int dflt) {
         return (!m->gram_f64 && env_int("SLIMB200_BATCH_NT", dflt) == 512) ? 512 : 256;
       };
-      classes.push_back({true, batch_cs_of(few_top ? 16 : 8), batch_nt_of(few_top ? 512 : 256), gram_top, 0, 0, 0});
+      classes.push_back({true, batch_cs_of(16), batch_nt_of(512), gram_top, 0, 0, 0});
       classes.push_back({true, batch_cs_of(8), batch_nt_of(256), gram_batch, 0, 0, 0});
       if (gram_cs > 1) classes.push_back({false, gram_cs, kGramNT, gram_heavy, 0, 0, 0});
       classes.push_back({false, 1, kGramNT, INT32_MIN, 0, 0, 0});
@@ -3223,6 +3189,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     CK(cudaEventCreate(&e1));
     CK(cudaEventCreate(&e2));
 
+    w_plan = wall();
     // ---- solve, retrying the (rare) columns that did not fit the output pool --------------------
     std::vector<int32_t> pending = order;  // indices into the caller's column list
     std::vector<int64_t> src_off(nsel, 0);
@@ -3425,6 +3392,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         cap = std::max<int64_t>(need + 1024, 1 << 20);
       }
       res->tm.solve_ms = solve_ms;
+      w_solved = wall();
 
       // ---- ordered gather into compact CSC (caller's column order) ------------------------------
       for (int32_t q = 0; q < nsel; q++) res->h_colptr[q + 1] = res->h_colptr[q] + cnt[q];
@@ -3483,10 +3451,15 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       cudaEventDestroy(e2);
       throw;
     }
+    w_gathered = wall();
     free_pools();
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaEventDestroy(e2);
+    if (env_int("SLIMB200_VERBOSE", 0) >= 2)
+      fprintf(stderr, "[slim-b200] learn(%d columns): host wall %.1f ms = plan+scratch %.1f | solve %.1f (kernels %.1f) | gather %.1f | "
+                      "release %.1f\n", nsel, wall() - w_start, w_plan - w_start, w_solved - w_plan, solve_ms, w_gathered - w_solved,
+              wall() - w_gathered);
     if (status) *status = kOk;
     return res;
   } catch (const EngineError &e) {

@@ -43,12 +43,15 @@ static Api *load() {
   static std::string why;
   if (!tried) {
     tried = true;
+    // 1. a copy that is already in the process (a torch process has its bundled NCCL loaded: use THAT one, two
+    //    NCCL builds with the same soname in one process do not mix); 2. SLIMB200_NCCL_LIBRARY; 3. the system's
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     const char *names[] = {getenv("SLIMB200_NCCL_LIBRARY"), "libnccl.so.2", "libnccl.so"};
     for (const char *n : names) {
-      if (!n || !*n) continue;
-      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
       if (api.handle) break;
-      why = dlerror();
+      if (!n || !*n) continue;
+      api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+      if (!api.handle) why = dlerror();
     }
     if (api.handle) {
 #define SLIM_NCCL_SYM(field, sym)                                                \

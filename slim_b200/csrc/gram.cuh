@@ -26,7 +26,6 @@
 
 constexpr int kGramNT = 256;
 constexpr int kGramNW = kGramNT / 32;
-constexpr int kGramUnroll = 16;  // independent gathered loads in flight per lane
 
 // ------------------------------------------------------------------------------------------------
 // Layout of G in HBM.  PANEL-major: a panel is kGramPW = 64 consecutive columns of all rows, rows contiguous
@@ -314,7 +313,7 @@ struct GatherStage {
   double val[32];
 };
 
-template <typename GA>
+template <typename GA, int UNR>
 __device__ __forceinline__ double gram_gather_sum(const typename GA::Col &col, const int32_t *sl_row,
                                                   const double *sl_val, int len, int first_chunk, int chunk_stride,
                                                   GatherStage &st) {
@@ -327,19 +326,20 @@ __device__ __forceinline__ double gram_gather_sum(const typename GA::Col &col, c
     st.val[lane] = e < len ? sl_val[e] : 0.0;  // entries past the end contribute 0 * G[0][col]
     __syncwarp();
     const int cnt = min(32, len - c * 32);
-    for (int i0 = 0; i0 < cnt; i0 += kGramUnroll) {
-      typename GA::Raw g[kGramUnroll];
+    for (int i0 = 0; i0 < cnt; i0 += UNR) {
+      typename GA::Raw g[UNR];  // UNR independent gathered loads in flight per lane
 #pragma unroll
-      for (int u = 0; u < kGramUnroll; u++) g[u] = GA::raw(col, st.row[i0 + u]);
+      for (int u = 0; u < UNR; u++) g[u] = GA::raw(col, st.row[i0 + u]);
 #pragma unroll
-      for (int u = 0; u < kGramUnroll; u++) acc = fma(st.val[i0 + u], GA::cvt(col, g[u]), acc);
+      for (int u = 0; u < UNR; u++) acc = fma(st.val[i0 + u], GA::cvt(col, g[u]), acc);
     }
   }
   return acc;
 }
 
-template <typename GA, int CS>
-__global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, const GramArgs ga) {
+// UNR = gathered loads in flight per lane: 16 with 64 registers (4 CTAs per SM) or 32 with 80 registers (3 CTAs per SM)
+template <typename GA, int CS, int UNR>
+__global__ void __launch_bounds__(kGramNT, UNR > 16 ? 3 : 4) cd_gram_kernel(const SolveArgs a, const GramArgs ga) {
   constexpr int NT = kGramNT, NW = kGramNW;
   using Tile = typename GA::Tile;
   __shared__ GramSmem<CS> sm;
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
           }
           // <a_m, yhat> for the 32 coordinates of the block: this warp's share of the sum over S
           const int len = sm.len;
-          sm.part[warp][lane] = gram_gather_sum<GA>(cab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW, s_stage[warp]);
+          sm.part[warp][lane] = gram_gather_sum<GA, UNR>(cab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW, s_stage[warp]);
           __syncthreads();
           if (warp == 0) {
             double ipf = 0.0;
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
               const double in_old = fabs(xn) > kEps ? xn : 0.0;
               const double ip = ipf - in_old * sq;  // cd.c:122-123 in one step
               const double num = aty - ip;
-              const double nx = num > a.l1r ? (num - a.l1r) / den : 0.0;
+              const double nx = num > a.l1r ? (num - a.l1r) / den : 0.0;  // (exact division: the reference's rounding, cd.c:127)
               const unsigned want = __ballot_sync(0xffffffffu, valid && lane >= k && nx != xn);
               if (!want) break;
               const int kk = __ffs(want) - 1;
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kGramNT, 4) cd_gram_kernel(const SolveArgs a, 
         const int e = cb * 32 + lane;
         const int col = sl_row[e < len ? e : 0];
         const double vk = e < len ? sl_val[e] : 0.0;
-        const double s = gram_gather_sum<GA>(GA::col(gv, col), sl_row, sl_val, len, warp, NW, s_stage[warp]);
+        const double s = gram_gather_sum<GA, UNR>(GA::col(gv, col), sl_row, sl_val, len, warp, NW, s_stage[warp]);
         hh = fma(vk, s, hh);
       }
     }

@@ -72,8 +72,9 @@ def test_c4_stratified_columns_match_oracle(c4, oracle):
 
 def test_c4_heaviest_columns_match_oracle(c4, oracle):
     # the 8 most popular items: every one of them goes through the batched Gram kernel at its full shape
-    # (16 CTAs x 512 threads, ~all 100 K coordinates active, 50 capped sweeps); 4 more from the one-target
-    # cluster class (2 000 <= nnz < 30 000) run next to them in the same call
+    # (16 CTAs x 512 threads, DMMA gather, ~all 100 K coordinates active, 50 capped sweeps); 4 more columns with
+    # 2 000 <= nnz < 30 000 run next to them in the same call: the two lighter ones on one-target clusters of 4 CTAs,
+    # the two heavier ones (>= 9 000 nonzeros) in a second, short batch
     staged, host = c4
     colcnt = np.bincount(host[1], minlength=staged.ncols)
     order = np.argsort(-colcnt, kind="stable")
