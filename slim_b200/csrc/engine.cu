@@ -189,6 +189,7 @@ struct Matrix {
 
 void free_matrix(Matrix *m) {
   if (!m) return;
+  const double w0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   int prev = -1;
   cudaGetDevice(&prev);
   cudaSetDevice(m->device);
@@ -213,6 +214,9 @@ void free_matrix(Matrix *m) {
   if (m->stream4) cudaStreamDestroy(m->stream4);
   if (m->stream) cudaStreamDestroy(m->stream);
   if (prev >= 0 && prev != m->device) cudaSetDevice(prev);  // leave the caller's current device as it was
+  if (getenv("SLIMB200_VERBOSE") && atoi(getenv("SLIMB200_VERBOSE")) >= 2)
+    fprintf(stderr, "[slim-b200] free_matrix(): host wall %.1f ms\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - w0);
   delete m;
 }
 
@@ -496,9 +500,14 @@ static int grid_for(int64_t n, int block, int sm_count) {
 
 static void build_gram(Matrix *m);  // defined next to the Gram kernels (gram.cuh)
 
+static double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *rowind,
               const float *rowval, bool on_device, int64_t nnz_if_device, int32_t *status) {
   Matrix *m = nullptr;
+  const double w0 = wall_ms();
   try {
     if (nrows < 0 || !rowptr) throw EngineError(kErrInput, "stage: bad nrows/rowptr");
     if (device < 0 || device >= device_count())
@@ -728,6 +737,9 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     m->stage_ms = ms;
+    if (getenv("SLIMB200_VERBOSE") && atoi(getenv("SLIMB200_VERBOSE")) >= 2)
+      fprintf(stderr, "[slim-b200] stage(): host wall %.1f ms, CUDA events %.1f ms (Gram build %.1f ms)\n", wall_ms() - w0, ms,
+              m->gram_ms);
     if (status) *status = kOk;
     return m;
   } catch (const EngineError &e) {
@@ -3064,6 +3076,9 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         if (hw < 1) throw EngineError(kErr, "learn: Gram kernel launch configuration not supported on this device");
         const int need = gc.batch ? (gc.ntargets + kBatchT - 1) / kBatchT : gc.ntargets;
         gc.units = std::min(hw, need);
+        // the batches are compute-bound (DMMA) and own their SMs; the one-target classes are memory-bound and need
+        // only a few SMs to keep the DRAM busy: SLIMB200_BATCH_UNITS caps the batches in flight so both overlap
+        if (gc.batch && env_int("SLIMB200_BATCH_UNITS", 0) > 0) gc.units = std::min(gc.units, env_int("SLIMB200_BATCH_UNITS", 0));
         gc.slot_base = slots;
         slots += gc.units * gc.cs;
         if (env_int("SLIMB200_VERBOSE", 0) && gc.ntargets > 0)

@@ -11,7 +11,7 @@ import sys
 from pathlib import Path
 
 LIB = Path(__file__).resolve().parent.parent / "slim_b200" / "lib" / "libslim.so"
-KEYS = ["UBLKCP", "LDGSTS", "LDGDEPBAR", "SYNCS", "MAPA", "UCGABAR", "DMMA", "DFMA", "HMMA", "UTCMMA", "RED", "ATOM", "PRMT",
+KEYS = ["UBLKCP", "LDGSTS", "LDGDEPBAR", "SYNCS", "MAPA", "UCGABAR", "DMMA", "DFMA", "HMMA", "UTCMMA", "RED", "REDG", "ATOM", "ATOMG", "PRMT",
         "I2F.F64", "SHFL", "BAR.SYNC", "LDG", "LDS", "STS", "ST.E"]
 
 
