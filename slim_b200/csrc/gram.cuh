@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(kGramNT, UNR > 16 ? 3 : 4) cd_gram_kernel(cons
               myslot = slotp[pm];
             }
             const double cn = (double)__ldg(a.cnorms + ab);
-            den = cn * cn + a.l2r;
+            den = 1.0 / (cn * cn + a.l2r);  // reciprocal of cnorm^2 + l2r (cd.c:127), taken off the chain's critical path
             sq = __ldg(a.csq + ab);
             aty = (double)(float)GA::at(cab, j);  // G[j][ab]; gk_fkv_t.key is a float (estimate.c:437)
           }
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(kGramNT, UNR > 16 ? 3 : 4) cd_gram_kernel(cons
               const double in_old = fabs(xn) > kEps ? xn : 0.0;
               const double ip = ipf - in_old * sq;  // cd.c:122-123 in one step
               const double num = aty - ip;
-              const double nx = num > a.l1r ? (num - a.l1r) / den : 0.0;  // (exact division: the reference's rounding, cd.c:127)
+              const double nx = num > a.l1r ? (num - a.l1r) * den : 0.0;
               const unsigned want = __ballot_sync(0xffffffffu, valid && lane >= k && nx != xn);
               if (!want) break;
               const int kk = __ffs(want) - 1;

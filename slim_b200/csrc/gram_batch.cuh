@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
             act[v] = (amask[(size_t)warp * nwords + (i >> 5)] >> (i & 31)) & 1u;
             if (i < a.ncols) {
               const double cn = (double)__ldg(a.cnorms + i);
-              den[v] = cn * cn + a.l2r;
+              den[v] = 1.0 / (cn * cn + a.l2r);  // reciprocal (cd.c:127), off the chain's critical path
               sq[v] = __ldg(a.csq + i);
             }
             aty[v] = (double)(float)gj[v];  // gk_fkv_t.key is a float (estimate.c:437)
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(NTB, NTB <= 256 ? 2 : 1) cd_gram_batch_kernel(
               in_old[v] = fabs(xn[v]) > kEps ? xn[v] : 0.0;
               const double ip = ipf[v] - in_old[v] * sq[v];
               const double num = aty[v] - ip;
-              nx[v] = num > a.l1r ? (num - a.l1r) / den[v] : 0.0;
+              nx[v] = num > a.l1r ? (num - a.l1r) * den[v] : 0.0;
               wm[v] = __ballot_sync(0xffffffffu, act[v] && (lane * V + v >= kpos) && nx[v] != xn[v]);
             }
             int ostar = 1 << 30;
