@@ -61,8 +61,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SLIM_BENCH_WORKLOAD", "c4"))
     ap.add_argument("--cols-per-step", type=int, default=int(os.environ.get("SLIM_BENCH_COLS", "0")),
-                    help="target columns per step PER GPU (0: 12288; 256 for c5, whose Gram matrix does not fit in "
-                         "HBM so that every target streams R)")
+                    help="target columns per step PER GPU (0: 12288; 4096 for c5)")
     ap.add_argument("--cpu-cols", type=int, default=int(os.environ.get("SLIM_BENCH_CPU_COLS", "0")),
                     help="columns per reference step (0: four per host thread)")
     ap.add_argument("--l1r", type=float, default=1.0)
@@ -285,7 +284,7 @@ def run_reference(args, rp, ri, rv, colcnt, steps, warmup, keep_w=None):
 def main():
     args = parse_args()
     if args.cols_per_step <= 0:
-        args.cols_per_step = 256 if args.workload == "c5" else 12288
+        args.cols_per_step = 4096 if args.workload == "c5" else 12288
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -419,51 +418,16 @@ def main():
             traffic = None
     gram_eb, gram_ms = staged.gram_info()
     gram_bytes, gram_h32, gram_h16 = staged.gram_layout()
-    kernel_name = ("cd_gram_kernel + cd_gram_batch_kernel (Gram-space CD, concurrent launches)" if gram_eb
+    gram_stair, gram_hd = staged.gram_stair()
+    kernel_name = ("cd_gram_kernel on the stair-layout Gram matrix + cd_cluster_kernel for the giant targets "
+                   "(concurrent launches)" if gram_stair else
+                   "cd_gram_kernel + cd_gram_batch_kernel (Gram-space CD, concurrent launches)" if gram_eb
                    else "cd_cluster_kernel (user-space CD)")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms_per_launch": solve_ms / n_launch,
                 "sweep_only_GBps": sweep_b / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0,
                 "mean_sweeps_per_column": float(np.mean(np.concatenate(sweeps_all))) if sweeps_all else 0.0}
-
-    # e2e: host buffers -> C ABI -> host result, copies inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        rp_h = rp_d.cpu().pin_memory().numpy()
-        ri_h = ri_d.cpu().pin_memory().numpy()
-        rv_h = rv_d.cpu().pin_memory().numpy()
-        h2d = rp_h.nbytes + ri_h.nbytes + rv_h.nbytes
-        d2h_total = 0
-
-        def e2e_step(s):
-            nonlocal d2h_total
-            cols = stratified_columns(colcnt, ncs_total, offset=s)
-            mine = shard_columns(cols, colcnt, rank, world)
-            with Staged(rp_h, ri_h, rv_h, device=local_rank) as st_:
-                res = learn_columns(st_, params, cols=cols[mine])
-                if world > 1:  # the all-gather is part of the job: every rank reads the WHOLE step's W back
-                    full = comm.all_gather_columns(res, mine, len(cols))
-                    res.close()
-                    res = full
-                w = res.to_host()
-                d2h_total += w["colptr"].nbytes + w["colind"].nbytes + w["colval"].nbytes
-                res.close()
-
-        e2e_step(0)
-        d2h_total = 0
-        barrier()
-        t0 = time.perf_counter()
-        for s in range(args.steps):
-            e2e_step(args.warmup + s)
-        barrier()
-        ew = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ew, op=dist.ReduceOp.MAX)
-        e2e = {"value": ncs_total * args.steps / float(ew.item()), "unit": "columns/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_total / max(args.steps, 1)),
-               "api": "SLIMB200_Stage + SLIMB200_LearnColumns" + (" + SLIMB200_AllGatherColumns" if world > 1 else "") +
-                      " + SLIMB200_ResultToHost (host buffers)"}
 
     cpu_baseline = None
     parity_check = None
@@ -509,6 +473,47 @@ def main():
         except Exception as ex:
             entry_point = {"failed": repr(ex)}
 
+    # e2e: host buffers -> C ABI -> host result, copies inside the timed region
+    # (the resident matrix is released first: two copies of a 133 GB stair-layout Gram matrix do not fit in HBM)
+    stage_ms_resident = staged.stage_ms
+    staged.close()
+    e2e = None
+    if not args.no_e2e:
+        rp_h = rp_d.cpu().pin_memory().numpy()
+        ri_h = ri_d.cpu().pin_memory().numpy()
+        rv_h = rv_d.cpu().pin_memory().numpy()
+        h2d = rp_h.nbytes + ri_h.nbytes + rv_h.nbytes
+        d2h_total = 0
+
+        def e2e_step(s):
+            nonlocal d2h_total
+            cols = stratified_columns(colcnt, ncs_total, offset=s)
+            mine = shard_columns(cols, colcnt, rank, world)
+            with Staged(rp_h, ri_h, rv_h, device=local_rank) as st_:
+                res = learn_columns(st_, params, cols=cols[mine])
+                if world > 1:  # the all-gather is part of the job: every rank reads the WHOLE step's W back
+                    full = comm.all_gather_columns(res, mine, len(cols))
+                    res.close()
+                    res = full
+                w = res.to_host()
+                d2h_total += w["colptr"].nbytes + w["colind"].nbytes + w["colval"].nbytes
+                res.close()
+
+        e2e_step(0)
+        d2h_total = 0
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            e2e_step(args.warmup + s)
+        barrier()
+        ew = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ew, op=dist.ReduceOp.MAX)
+        e2e = {"value": ncs_total * args.steps / float(ew.item()), "unit": "columns/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_total / max(args.steps, 1)),
+               "api": "SLIMB200_Stage + SLIMB200_LearnColumns" + (" + SLIMB200_AllGatherColumns" if world > 1 else "") +
+                      " + SLIMB200_ResultToHost (host buffers)"}
+
     if rank == 0:
         line = dict(base, value=value, ms_per_step=1e3 * wall / args.steps,
                     config={"workload": wl_name, "cols_per_step_per_gpu": args.cols_per_step,
@@ -518,16 +523,17 @@ def main():
                             "l2_policy": ("inputs >> 126 MB L2 (the solver streams the %.0f GB Gram matrix, tens of TB of DRAM traffic "
                                           "per step); different columns every step" % (gram_bytes / 1e9) if gram_eb else
                                           "inputs (2 GB CSR+CSC) >> 126 MB L2; different columns every step"),
-                            "datagen_s": round(gen_s, 2), "stage_ms": round(staged.stage_ms, 2),
+                            "datagen_s": round(gen_s, 2), "stage_ms": round(stage_ms_resident, 2),
                             "gram": {"layout": ("packed unsigned: 32-bit columns [0,%d), 16-bit [%d,%d), 8-bit beyond"
-                                                % (gram_h32, gram_h32, gram_h16)) if gram_eb == 4 else
+                                                % (gram_h32, gram_h32, gram_h16) +
+                                                (", STAIR layout: panel p stores rows [0, max(64(p+1), %d))" % gram_hd
+                                                 if gram_stair else "")) if gram_eb == 4 else
                                                ("fp64" if gram_eb == 8 else "not staged"),
                                      "build_ms": round(gram_ms, 1), "GB": round(gram_bytes / 1e9, 2)}},
                     roofline=roofline, cpu_baseline=cpu_baseline, parity_check=parity_check, e2e=e2e,
                     slim_learn_entry_point=entry_point, clocks=clocks,
                     gpu_launches=int(launches))
         print(json.dumps(line))
-    staged.close()
     if world > 1:
         comm.close()
         dist.destroy_process_group()

@@ -61,6 +61,12 @@ int32_t SLIMB200_MatrixGram(const slimb200_matrix_t *matrix, void *out);
  * [h32, h16) 16-bit, the rest 8-bit; a column's width follows from the bound G[k][i] <= rmax * sum_u r_ui^2.
  * h32 = h16 = 0 for the fp64 layout.  Any pointer may be NULL. */
 int32_t SLIMB200_MatrixGramLayout(const slimb200_matrix_t *matrix, int64_t *bytes, int32_t *h32, int32_t *h16);
+/* STAIR layout: when the full packed matrix does not fit in HBM (BASELINE configs[4]: 500 K items = 308 GB) staging
+ * keeps, for every panel p of 64 columns, only the rows [0, max(64 (p + 1), hd)) -- the upper triangle by panels plus
+ * a full square of the hd most popular items (133 GB for configs[4]); G is symmetric, so an element that is not
+ * stored is read as its mirror image.  stair = 1 when this layout is in use, hd = side of the square.
+ * SLIMB200_GRAM_LAYOUT=stair|full forces / forbids it, SLIMB200_GRAM_HD sets hd (default 32768). */
+int32_t SLIMB200_MatrixGramStair(const slimb200_matrix_t *matrix, int32_t *stair, int32_t *hd);
 
 /* Solve target columns cols[0..ncols_sel) (cols == NULL: every column): the per-column body of
  * EstimateModelCD (reference src/libslim/estimate.c:405-505) + CoordinateDescent (cd.c:101-142).

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "SLIMB200_MatrixGramInfo": (C.c_int32, [C.c_void_p, c_i32p, c_f64p]),
     "SLIMB200_MatrixGram": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "SLIMB200_MatrixGramLayout": (C.c_int32, [C.c_void_p, c_i64p, c_i32p, c_i32p]),
+    "SLIMB200_MatrixGramStair": (C.c_int32, [C.c_void_p, c_i32p, c_i32p]),
     "SLIMB200_LearnColumns": (C.c_void_p, [C.c_void_p, c_i32p, c_f64p, c_i32p, C.c_int32, C.c_void_p, c_i32p]),
     "SLIMB200_FreeResult": (None, [C.POINTER(C.c_void_p)]),
     "SLIMB200_ResultInfo": (C.c_int32, [C.c_void_p, c_i32p, c_i64p, c_f64p, c_f64p, c_i32p]),

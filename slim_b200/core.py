@@ -358,6 +358,12 @@ class Staged:
         assert self._lib.SLIMB200_MatrixGramLayout(self.handle, C.byref(b), C.byref(h32), C.byref(h16)) == SLIM_OK
         return b.value, h32.value, h16.value
 
+    def gram_stair(self):
+        """(stair, hd): stair = 1 when G is held in the STAIR layout (panel p stores rows [0, max(64(p+1), hd)) only)."""
+        st, hd = C.c_int32(0), C.c_int32(0)
+        assert self._lib.SLIMB200_MatrixGramStair(self.handle, C.byref(st), C.byref(hd)) == SLIM_OK
+        return st.value, hd.value
+
     def gram(self):
         """Dense copy of the staged Gram matrix (internal item order), None when it was not staged."""
         eb, _ = self.gram_info()

@@ -1116,6 +1116,12 @@ int32_t SLIMB200_MatrixGramLayout(const slimb200_matrix_t *matrix, int64_t *byte
   return SLIM_OK;
 }
 
+int32_t SLIMB200_MatrixGramStair(const slimb200_matrix_t *matrix, int32_t *stair, int32_t *hd) {
+  if (!matrix) return SLIM_ERROR_INPUT;
+  matrix_gram_stair(reinterpret_cast<const Matrix *>(matrix), stair, hd);
+  return SLIM_OK;
+}
+
 int32_t SLIMB200_MatrixGram(const slimb200_matrix_t *matrix, void *out) {
   if (!matrix || !out) return SLIM_ERROR_INPUT;
   return matrix_gram_to_host(reinterpret_cast<const Matrix *>(matrix), out);

@@ -172,12 +172,18 @@ struct Matrix {
   size_t gram_bytes = 0;
   int32_t gram_h32 = 0, gram_h16 = 0;      // packed layout: first 16-bit / 8-bit column (gram.cuh: GramView)
   size_t gram_off16 = 0, gram_off8 = 0;    // packed layout: byte offsets of the 16-bit / 8-bit column ranges
+  // STAIR layout (gram.cuh: GaStair), used when the full matrix does not fit: panel p stores rows [0, max(64(p+1), hd))
+  bool gram_stair = false;
+  int32_t gram_hd = 0;
+  unsigned long long *d_gram_pbase = nullptr;   // byte offset of every panel
+  std::vector<unsigned long long> h_gram_pbase;
   unsigned long long *d_expand = nullptr;  // per item: sum of len(row_u) over the users of the column
   double gram_ms = 0.0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // extra streams: the Gram launches of the target classes run side by side
   cudaStream_t stream3 = nullptr;
   cudaStream_t stream4 = nullptr;
+  cudaStream_t stream5 = nullptr;
   int sm_count = 0;
   int smem_optin = 0;
   double stage_ms = 0.0;
@@ -208,10 +214,12 @@ void free_matrix(Matrix *m) {
   cudaFree(m->d_inv);
   cudaFree(m->d_scratch);
   cudaFree(m->d_gram);
+  cudaFree(m->d_gram_pbase);
   cudaFree(m->d_expand);
   if (m->stream2) cudaStreamDestroy(m->stream2);
   if (m->stream3) cudaStreamDestroy(m->stream3);
   if (m->stream4) cudaStreamDestroy(m->stream4);
+  if (m->stream5) cudaStreamDestroy(m->stream5);
   if (m->stream) cudaStreamDestroy(m->stream);
   if (prev >= 0 && prev != m->device) cudaSetDevice(prev);  // leave the caller's current device as it was
   if (getenv("SLIMB200_VERBOSE") && atoi(getenv("SLIMB200_VERBOSE")) >= 2)
@@ -524,6 +532,7 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
     CK(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m->stream3, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m->stream4, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&m->stream5, cudaStreamNonBlocking));
     cudaStream_t s = m->stream;
     m->nrows = nrows;
     m->nnz = on_device ? nnz_if_device : (int64_t)rowptr[nrows];
@@ -780,6 +789,11 @@ void matrix_gram_info(const Matrix *m, int32_t *elem_bytes, double *build_ms) {
   if (build_ms) *build_ms = m->gram_ms;
 }
 
+void matrix_gram_stair(const Matrix *m, int32_t *stair, int32_t *hd) {
+  if (stair) *stair = (m->d_gram && m->gram_stair) ? 1 : 0;
+  if (hd) *hd = (m->d_gram && m->gram_stair) ? m->gram_hd : 0;
+}
+
 void matrix_gram_layout(const Matrix *m, int64_t *bytes, int32_t *h32, int32_t *h16) {
   if (bytes) *bytes = m->d_gram ? (int64_t)m->gram_bytes : 0;
   if (h32) *h32 = m->gram_f64 ? 0 : m->gram_h32;
@@ -800,6 +814,20 @@ int matrix_gram_to_host(const Matrix *m, void *out) {
       const double *g = reinterpret_cast<const double *>(raw.data());
       for (size_t k = 0; k < n; k++)
         for (size_t i = 0; i < n; i++) o[k * n + i] = g[gram_off(n, (int)k, (int)i)];
+    } else if (m->gram_stair) {
+      // stair layout: element (k, i) is row k of column i when stored, else row i of column k (gram.cuh: GaStair)
+      float *o = static_cast<float *>(out);
+      const size_t h32 = (size_t)m->gram_h32, h16 = (size_t)m->gram_h16, hd = (size_t)m->gram_hd;
+      auto elem = [&](size_t r, size_t c) -> uint32_t {
+        const size_t w = c < h32 ? 4 : (c < h16 ? 2 : 1);
+        const unsigned char *src = raw.data() + m->h_gram_pbase[c >> 6] + r * kGramPW * w + (c & 63) * w;
+        uint32_t v = 0;
+        memcpy(&v, src, w);
+        return v;
+      };
+      for (size_t k = 0; k < n; k++)
+        for (size_t i = 0; i < n; i++)
+          o[k * n + i] = (float)((k < hd || (k >> 6) <= (i >> 6)) ? elem(k, i) : elem(i, k));
     } else {
       float *o = static_cast<float *>(out);
       const size_t h32 = (size_t)m->gram_h32, h16 = (size_t)m->gram_h16;
@@ -2470,7 +2498,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
 // ------------------------------------------------------------------------------------------------
 // K0g host side: decide whether G fits, pick its element type, build it (part of staging).
 //   SLIMB200_GRAM=0        never build G (the user-space kernels are used)
-//   SLIMB200_GRAM_GB=n     upper bound for G in GiB (default 100); G must also fit the free memory
+//   SLIMB200_GRAM_GB=n     upper bound for G in GiB (default 150); G must also fit the free memory minus a reserve
 //   SLIMB200_GRAM_F64=1    force double elements
 // ------------------------------------------------------------------------------------------------
 static int env_int(const char *name, int dflt);
@@ -2527,16 +2555,40 @@ static void build_gram(Matrix *m) {
   const size_t nr = (size_t)ncols;
   const size_t off16 = (h32 / kGramPW) * nr * (kGramPW * 4);
   const size_t off8 = off16 + ((h16 - h32) / kGramPW) * nr * (kGramPW * 2);
-  const size_t bytes = packed ? off8 + ((ld - h16) / kGramPW) * nr * kGramPW + 16  // (+16: word loads at the very end)
+  size_t bytes = packed ? off8 + ((ld - h16) / kGramPW) * nr * kGramPW + 16  // (+16: word loads at the very end)
                               : npan * nr * kGramPW * sizeof(double);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t budget = (size_t)env_int("SLIMB200_GRAM_GB", 120) << 30;
   // leave room for the solve scratch and the result pools
-  const size_t reserve = (size_t)16 << 30;
-  if (bytes > budget || bytes + std::min(reserve, total_b / 4) > free_b) {
+  const size_t reserve = std::min((size_t)16 << 30, total_b / 4);
+  const size_t budget = std::min((size_t)env_int("SLIMB200_GRAM_GB", 150) << 30, free_b > reserve ? free_b - reserve : 0);
+  // Full matrix if it fits; otherwise -- packed elements only -- the STAIR layout (gram.cuh: GaStair), half the bytes:
+  // panel p keeps rows [0, max(64 (p + 1), hd)).  SLIMB200_GRAM_LAYOUT=stair forces it (tests), =full forbids it;
+  // SLIMB200_GRAM_HD = side of the full square of the most popular items (default 32768).
+  const char *lay = getenv("SLIMB200_GRAM_LAYOUT");
+  const bool force_stair = lay && !strcmp(lay, "stair"), no_stair = lay && !strcmp(lay, "full");
+  bool stair = false;
+  size_t hd = 0;
+  std::vector<unsigned long long> pbase;
+  if (packed && !no_stair && (force_stair || bytes > budget)) {
+    hd = (size_t)std::max(64, env_int("SLIMB200_GRAM_HD", 32768));
+    hd = std::min((hd + kGramPW - 1) / kGramPW * kGramPW, ld);
+    pbase.resize(npan + 1);
+    size_t o = 0;
+    for (size_t pnl = 0; pnl < npan; pnl++) {
+      pbase[pnl] = o;
+      const size_t rows = std::min(nr, std::max((pnl + 1) * kGramPW, hd));
+      const size_t w = pnl * kGramPW < h32 ? 4 : (pnl * kGramPW < h16 ? 2 : 1);
+      o += rows * kGramPW * w;
+    }
+    pbase[npan] = o;
+    bytes = o + 16;
+    stair = true;
+  }
+  if (bytes > budget) {
     if (env_int("SLIMB200_VERBOSE", 0))
-      fprintf(stderr, "[slim-b200] Gram matrix (%.1f GB) does not fit: user-space kernels will be used\n", bytes / 1e9);
+      fprintf(stderr, "[slim-b200] Gram matrix (%.1f GB%s) does not fit (budget %.1f GB): user-space kernels will be used\n",
+              bytes / 1e9, stair ? ", stair layout" : "", budget / 1e9);
     return;
   }
   EventPair ev;
@@ -2557,7 +2609,16 @@ static void build_gram(Matrix *m) {
   m->gram_h16 = (int32_t)h16;
   m->gram_off16 = off16;
   m->gram_off8 = off8;
-  GramView gv{static_cast<const unsigned char *>(m->d_gram), nr, m->gram_h32, m->gram_h16, off16, off8};
+  GramView gv{static_cast<const unsigned char *>(m->d_gram), nr, m->gram_h32, m->gram_h16, off16, off8, nullptr, 0};
+  if (stair) {
+    CK(cudaMalloc(&m->d_gram_pbase, sizeof(unsigned long long) * pbase.size()));
+    CK(cudaMemcpyAsync(m->d_gram_pbase, pbase.data(), sizeof(unsigned long long) * pbase.size(), cudaMemcpyHostToDevice, s));
+    m->gram_stair = true;
+    m->gram_hd = (int32_t)hd;
+    m->h_gram_pbase = pbase;
+    gv.pbase = m->d_gram_pbase;
+    gv.hd = m->gram_hd;
+  }
   // work items (column, entry range), heaviest columns first (internal ids are in popularity order)
   constexpr int32_t kSeg = 2048;
   std::vector<int32_t> wc, w0, w1;
@@ -2580,7 +2641,9 @@ static void build_gram(Matrix *m) {
 #define SLIM_GRAM_BUILD(GB, HV)                                                                               \
   gram_build_kernel<GB, HV><<<grid, 256, 0, s>>>(nwork, d_wc.p, d_w0.p, d_w1.p, m->d_colptr, m->d_colind,      \
                                                  m->d_colval, m->d_rowptr, m->d_rowind, m->d_rowval, gv, m->d_expand)
-    if (packed) {
+    if (stair) {
+      if (kv) SLIM_GRAM_BUILD(GbStair, true); else SLIM_GRAM_BUILD(GbStair, false);
+    } else if (packed) {
       if (kv) SLIM_GRAM_BUILD(GbPacked, true); else SLIM_GRAM_BUILD(GbPacked, false);
     } else {
       if (kv) SLIM_GRAM_BUILD(GbF64, true); else SLIM_GRAM_BUILD(GbF64, false);
@@ -2596,7 +2659,8 @@ static void build_gram(Matrix *m) {
   m->gram_ms = ms;
   if (env_int("SLIMB200_VERBOSE", 0))
     fprintf(stderr, "[slim-b200] Gram matrix: %d x %zu %s, %.2f GB (32-bit columns %zu, 16-bit %zu, 8-bit %zu), %d work "
-                    "items, built in %.1f ms\n", ncols, ld, packed ? "packed unsigned (exact)" : "fp64", bytes / 1e9,
+                    "items, built in %.1f ms\n", ncols, ld,
+            stair ? "packed unsigned (exact), STAIR layout" : packed ? "packed unsigned (exact)" : "fp64", bytes / 1e9,
             packed ? h32 : 0, packed ? h16 - h32 : 0, packed ? ld - h16 : 0, nwork, ms);
 }
 
@@ -2827,6 +2891,11 @@ static int gram_launch_t(const SolveArgs &args, const GramArgs &gargs, int count
 
 static int gram_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &gargs, int count, cudaStream_t s,
                        bool query_only) {
+  if (gargs.gv.pbase) {  // stair layout: single CTAs and clusters of 4
+    if (cs == 1) return gram_launch_t<GaStair, 1, 16>(args, gargs, count, s, query_only);
+    if (cs == 4) return gram_launch_t<GaStair, 4, 16>(args, gargs, count, s, query_only);
+    throw EngineError(kErr, "gram_launch: the stair layout supports cluster sizes 1 and 4");
+  }
   // the deep-unroll variant exists for the packed layout and the two default shapes (single CTA, clusters of 4)
   const bool deep = !f64 && (cs == 1 || cs == 4) && env_int("SLIMB200_GRAM_UNROLL", 32) == 32;
   if (deep) {
@@ -2979,7 +3048,17 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     // yhat too large for shared memory: thread-block clusters with yhat resident in L2
     int cs = env_int("SLIMB200_CLUSTER", plan.ysmem ? 0 : 16);
     if (cs != 0 && cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) cs = 16;
-    if (use_gram) cs = 0;
+    // STAIR layout of G (build_gram): the one-target Gram kernels solve every target below SLIMB200_STAIR_USER
+    // nonzeros; the giants above it (their sweeps would gather |S| x |A| ~ 10^10 elements, more than the nnz(R) a
+    // user-space sweep streams) go to the user-space cluster kernel, launched side by side with the Gram classes
+    const bool stair = use_gram && m->gram_stair;
+    const int stair_user = (stair && !fslim) ? env_int("SLIMB200_STAIR_USER", 30000) : INT32_MAX;
+    int32_t n_user = 0;
+    if (stair)
+      for (int32_t q = 0; q < nsel; q++) n_user += m->h_colcnt[m->h_rank[colof(q)]] >= stair_user ? 1 : 0;
+    const bool mixed = n_user > 0;
+    if (mixed && cs == 0) cs = 16;
+    if (use_gram && !mixed) cs = 0;
     const bool use_cluster = cs > 0;
     const bool use_window = use_cluster && env_int("SLIMB200_WINDOW", 1) != 0;
     const size_t col_stride = use_gram ? m->gram_ld : (((size_t)std::max(ncols, 1) + 3) & ~size_t(3));
@@ -2995,13 +3074,15 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       // then comes from HBM, which still beats leaving most SMs idle
       nclusters = std::min(hw, std::max(by_l2, 8));
       if (env_int("SLIMB200_NCLUSTERS", 0) > 0) nclusters = env_int("SLIMB200_NCLUSTERS", 0);
-      nclusters = std::max(1, std::min(std::min(nclusters, hw), std::max(nsel, 1)));
+      nclusters = std::max(1, std::min(std::min(nclusters, hw), std::max(mixed ? n_user : nsel, 1)));
       plan.grid = nclusters * cs;
       if (env_int("SLIMB200_VERBOSE", 0))
         fprintf(stderr, "[slim-b200] cluster kernel: cluster=%d CTAs x %d threads, %d clusters in flight (hw max %d, "
                         "L2 budget allows %d), values=%d, window sweep=%d\n", cs, kClusterNT, nclusters, hw, by_l2,
                 (int)kernel_vals, (int)use_window);
-    } else if (!use_gram) {
+    }
+    const int user_grid = use_cluster ? nclusters * cs : 0;  // CTAs of the user-space cluster launch
+    if (!use_cluster && !use_gram) {
       int bps = 1;
       dispatch_solve(args, plan, kernel_vals, s, true, &bps);
       bps = std::max(1, bps);
@@ -3051,12 +3132,18 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       auto batch_nt_of = [&](int dflt) {
         return (!m->gram_f64 && env_int("SLIMB200_BATCH_NT", dflt) == 512) ? 512 : 256;
       };
-      classes.push_back({true, batch_cs_of(16), batch_nt_of(512), gram_top, 0, 0, 0});
-      classes.push_back({true, batch_cs_of(8), batch_nt_of(256), gram_batch, 0, 0, 0});
+      if (stair) {
+        gargs.gv.pbase = m->d_gram_pbase;  // (gram_launch picks the accessor from it, also for the occupancy queries)
+        if (gram_cs != 1) gram_cs = 4;
+      } else {
+        classes.push_back({true, batch_cs_of(16), batch_nt_of(512), gram_top, 0, 0, 0});
+        classes.push_back({true, batch_cs_of(8), batch_nt_of(256), gram_batch, 0, 0, 0});
+      }
       if (gram_cs > 1) classes.push_back({false, gram_cs, kGramNT, gram_heavy, 0, 0, 0});
       classes.push_back({false, 1, kGramNT, INT32_MIN, 0, 0, 0});
       for (int32_t q = 0; q < nsel; q++) {
         const int32_t c = m->h_colcnt[m->h_rank[colof(q)]];
+        if (c >= stair_user) continue;  // user-space cluster kernel
         for (auto &gc : classes)
           if (c >= gc.min_nnz) {
             gc.ntargets++;
@@ -3083,30 +3170,36 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         slots += gc.units * gc.cs;
         if (env_int("SLIMB200_VERBOSE", 0) && gc.ntargets > 0)
           fprintf(stderr, "[slim-b200] Gram-space (%s G): %d targets with nnz >= %d -> %s, %d x (%d CTAs x %d threads)\n",
-                  m->gram_f64 ? "fp64" : "packed", gc.ntargets, gc.min_nnz,
+                  m->gram_f64 ? "fp64" : (stair ? "packed, stair layout" : "packed"), gc.ntargets, gc.min_nnz,
                   gc.batch ? "cd_gram_batch_kernel (8 targets per cluster)" : "cd_gram_kernel", gc.units, gc.cs, gc.nt);
       }
       plan.grid = std::max(1, slots);
+      if (mixed && env_int("SLIMB200_VERBOSE", 0))
+        fprintf(stderr, "[slim-b200] stair layout: %d targets with nnz >= %d -> user-space cd_cluster_kernel\n", n_user,
+                stair_user);
     }
 
     // ---- scratch (cached on the matrix) --------------------------------------------------------
-    const size_t g = use_cluster ? (size_t)nclusters : (size_t)plan.grid;  // scratch slots
+    // user-space slots first (clusters, or CTAs of the team kernel), then the Gram slots (CTAs)
+    const size_t gu = use_cluster ? (size_t)nclusters : (use_gram ? 0 : (size_t)plan.grid);
+    const size_t gg = use_gram ? (size_t)plan.grid : 0;
+    const size_t gux = use_cluster ? (size_t)user_grid : gu;  // the cluster kernel keeps one copy of x per CTA
     size_t off = 0;
     auto carve = [&](size_t bytes) {
       size_t o = off;
       off += (bytes + 255) & ~size_t(255);
       return o;
     };
-    const size_t o_acc = carve(use_gram ? 0 : g * col_stride * sizeof(double));
-    const size_t o_xw = carve(g * col_stride * sizeof(float));
-    const size_t o_yh = carve(((plan.ysmem && !use_cluster) || use_gram) ? 0 : g * row_stride * sizeof(double));
+    const size_t o_acc = carve(gu * col_stride * sizeof(double));
+    const size_t o_xw = carve((gu + gg) * col_stride * sizeof(float));
+    const size_t o_yh = carve((plan.ysmem && !use_cluster) ? 0 : gu * row_stride * sizeof(double));
     const size_t zero_bytes = off;  // acc, xw, yhat must start at zero
-    const size_t o_meta = carve(use_gram ? 0 : g * col_stride * (use_cluster ? sizeof(ActMetaC) : sizeof(ActMeta)));
-    const size_t o_x = carve((use_cluster ? (size_t)plan.grid : g) * col_stride * sizeof(double));
-    const size_t o_idx = carve(g * col_stride * sizeof(int32_t));
-    const size_t o_gslot = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
-    const size_t o_grow = carve(use_gram ? g * col_stride * sizeof(int32_t) : 0);
-    const size_t o_gval = carve(use_gram ? g * col_stride * sizeof(double) : 0);
+    const size_t o_meta = carve(gu * col_stride * (use_cluster ? sizeof(ActMetaC) : sizeof(ActMeta)));
+    const size_t o_x = carve((gux + gg) * col_stride * sizeof(double));
+    const size_t o_idx = carve((gu + gg) * col_stride * sizeof(int32_t));
+    const size_t o_gslot = carve(gg * col_stride * sizeof(int32_t));
+    const size_t o_grow = carve(gg * col_stride * sizeof(int32_t));
+    const size_t o_gval = carve(gg * col_stride * sizeof(double));
     size_t nbcta = 0;  // the batch classes come first: their CTAs use slots 0 .. nbcta-1
     for (const auto &gc : classes)
       if (gc.batch) nbcta += (size_t)gc.units * gc.cs;
@@ -3116,7 +3209,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     const size_t o_bam = carve(nbcta * kBatchT * nwords * sizeof(uint32_t));
     const size_t o_ban = carve(nbcta * nwords * sizeof(uint32_t));
     const size_t grp_stride = (size_t)(ncols + 31) / 32 + 1;
-    const size_t o_grp = carve(use_cluster ? g * grp_stride * sizeof(GroupMeta) : 0);
+    const size_t o_grp = carve(use_cluster ? gu * grp_stride * sizeof(GroupMeta) : 0);
     if (off > m->scratch_bytes) {
       cudaFree(m->d_scratch);
       m->d_scratch = nullptr;
@@ -3181,9 +3274,9 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     args.act_idx = reinterpret_cast<int32_t *>(sb + o_idx);
     if (use_gram) {
       gargs.gv = GramView{static_cast<const unsigned char *>(m->d_gram), (size_t)ncols, m->gram_h32, m->gram_h16,
-                          m->gram_off16, m->gram_off8};
-      gargs.act = reinterpret_cast<int32_t *>(sb + o_idx);
-      gargs.x = reinterpret_cast<double *>(sb + o_x);
+                          m->gram_off16, m->gram_off8, stair ? m->d_gram_pbase : nullptr, stair ? m->gram_hd : 0};
+      gargs.act = reinterpret_cast<int32_t *>(sb + o_idx) + gu * col_stride;
+      gargs.x = reinterpret_cast<double *>(sb + o_x) + gux * col_stride;
       gargs.slotp = reinterpret_cast<int32_t *>(sb + o_gslot);
       gargs.sl_row = reinterpret_cast<int32_t *>(sb + o_grow);
       gargs.sl_val = reinterpret_cast<double *>(sb + o_gval);
@@ -3237,7 +3330,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         DevBuf<int32_t> d_ng;
         DevBuf<unsigned long long> d_used;
         d_targets.alloc(nt);
-        d_queue.alloc_zero(4, s);
+        d_queue.alloc_zero(8, s);
         d_used.alloc_zero(1, s);
         d_ocnt.alloc(nt);
         d_ooff.alloc(nt);
@@ -3315,7 +3408,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         }
         if (use_gram) {
           // `pending` is sorted by descending column nnz: the classes are consecutive ranges
-          cudaStream_t streams[4] = {s, m->stream2, m->stream3, m->stream4};
+          cudaStream_t streams[5] = {s, m->stream2, m->stream3, m->stream4, m->stream5};
           int used = 0;
           // fork point: the side streams wait for the copies / memsets queued on s so far, NOT for the
           // launches that follow on s (the classes must overlap)
@@ -3327,6 +3420,19 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
             return st;
           };
           int32_t q_next = 0;
+          if (mixed) {
+            // stair layout: the giants at the head of the list go to the user-space cluster kernel
+            while (q_next < nt && m->h_colcnt[tcols[q_next]] >= stair_user) q_next++;
+            if (q_next > 0) {
+              SolveArgs ua = args;
+              ua.ntargets = q_next;
+              ua.queue = d_queue.p + 7;
+              cluster_dispatch(kernel_vals, use_window, ua, cargs, cs, std::min(nclusters, (int)q_next), next_stream(), false);
+            }
+          }
+          // the Gram kernels index their scratch slots from the end of the user-space slots
+          SolveArgs ga_args = args;
+          ga_args.xw = args.xw + gu * col_stride;
           int ci = 0;
           for (const auto &gc : classes) {
             int32_t q_end = q_next;
@@ -3340,8 +3446,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
               gq.slot_base = gc.slot_base;
               const int need = gc.batch ? (ncl_targets + kBatchT - 1) / kBatchT : ncl_targets;
               const int units = std::max(1, std::min(gc.units, need));
-              if (gc.batch) batch_launch(m->gram_f64, gc.cs, gc.nt, args, gq, bargs, units, next_stream(), false);
-              else gram_launch(m->gram_f64, gc.cs, args, gq, units, next_stream(), false);
+              if (gc.batch) batch_launch(m->gram_f64, gc.cs, gc.nt, ga_args, gq, bargs, units, next_stream(), false);
+              else gram_launch(m->gram_f64, gc.cs, ga_args, gq, units, next_stream(), false);
             }
             q_next = q_end;
             ci++;

@@ -64,6 +64,9 @@ int matrix_gram_to_host(const Matrix *m, void *out);
 // Footprint of the staged Gram matrix in HBM and the column ranges of the packed layout: 32-bit elements for
 // columns [0, h32), 16-bit for [h32, h16), 8-bit from h16 on (zeros for the fp64 layout).
 void matrix_gram_layout(const Matrix *m, int64_t *bytes, int32_t *h32, int32_t *h16);
+// stair = 1 when the packed matrix is held in the STAIR layout (panel p stores rows [0, max(64(p+1), hd)) only: the
+// layout for item counts whose full matrix does not fit), hd = side of its full head square.
+void matrix_gram_stair(const Matrix *m, int32_t *stair, int32_t *hd);
 
 Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel,
               const WarmStart *warm, int32_t *status);

@@ -45,10 +45,21 @@ struct GramView {
   size_t nr;           // rows of G (= ncols)
   int32_t h32, h16;    // packed layout: first column of the 16-bit / 8-bit range (multiples of kGramPW)
   size_t off16, off8;  // packed layout: byte offsets of the 16-bit / 8-bit ranges
+  // STAIR layout (GaStair below; nullptr / 0 for the full layouts): byte offset of every panel, and the number of
+  // leading rows that every panel stores
+  const unsigned long long *pbase;
+  int32_t hd;
 };
 
 // fp64 elements, one range: element (k, i) at gram_off(nr, k, i)
+struct GatherStage {  // (row, value) pairs of a 32-entry chunk of the nonzero list, one slice per warp
+  int row[32];
+  double val[32];
+};
+
 struct GaF64 {
+  static constexpr bool kStair = false;
+  using Stage = GatherStage;
   using Tile = double;                          // element type of the in-block Gram tiles in shared memory
   static constexpr int kMaxRowBytes = kGramPW * 8;  // bytes of one panel row
   struct Col {
@@ -61,6 +72,7 @@ struct GaF64 {
   static __device__ __forceinline__ Raw raw(const Col &c, int r) { return __ldg(c.p + (size_t)(uint32_t)r * kGramPW); }
   static __device__ __forceinline__ double cvt(const Col &, Raw w) { return w; }
   static __device__ __forceinline__ double at(const Col &c, int r) { return raw(c, r); }
+  static __device__ __forceinline__ double at(const GramView &, const Col &c, int r) { return raw(c, r); }
   static __device__ __forceinline__ double at(const GramView &g, int k, int i) {
     return __ldg(reinterpret_cast<const double *>(g.base) + gram_off(g.nr, k, i));
   }
@@ -78,6 +90,8 @@ struct GaF64 {
 
 // packed unsigned elements, three column ranges
 struct GaPacked {
+  static constexpr bool kStair = false;
+  using Stage = GatherStage;
   using Tile = float;  // exact: every entry is an integer below 2^24 ... or the tile holds it as float anyway
   static constexpr int kMaxRowBytes = kGramPW * 4;
   struct Col {
@@ -123,6 +137,7 @@ struct GaPacked {
   }
   static __device__ __forceinline__ double cvt(const Col &c, Raw w) { return (double)__byte_perm(w, 0u, c.sel); }
   static __device__ __forceinline__ double at(const Col &c, int r) { return cvt(c, raw(c, r)); }
+  static __device__ __forceinline__ double at(const GramView &, const Col &c, int r) { return cvt(c, raw(c, r)); }
   static __device__ __forceinline__ double at(const GramView &g, int k, int i) {
     uint32_t stride, wlog;
     const size_t byte = col_byte(g, i, stride, wlog) + (size_t)k * stride;
@@ -154,6 +169,65 @@ struct GaPacked {
     uint32_t stride, wlog;
     return g.base + col_byte(g, item0, stride, wlog);
   }
+};
+
+// ------------------------------------------------------------------------------------------------
+// STAIR layout: the packed layout for item counts whose full N x N matrix does not fit in HBM (C5: 500 K items would
+// need 291 GB).  G is symmetric, so panel p (columns 64p .. 64p+63) stores only the rows
+//     [0, max(64 (p + 1), hd))            (clamped to ncols),
+// i.e. the upper triangle by panels plus a full square of the hd most popular items.  Element (k, i) is read as
+// row k of column i when that is stored (k < hd or panel(k) <= panel(i)) and as row i of column k otherwise.
+// Active sets consist mostly of popular items, so almost every gathered pair falls into the square (same access
+// pattern as the full layout); the triangle costs one DRAM sector per gathered element.  Half the bytes of the full
+// layout: 128 GB for C5.  Panel offsets come from a table (pbase, 8 bytes per panel).
+// ------------------------------------------------------------------------------------------------
+struct GatherStageStair : GatherStage {
+  const unsigned char *kp[32];  // the entry's own column: word address of (row 0, column k) ...
+  uint2 ks[32];                 // ... its row stride and PRMT selector
+};
+
+struct GaStair {
+  static constexpr bool kStair = true;
+  using Stage = GatherStageStair;
+  using Tile = float;
+  static constexpr int kMaxRowBytes = kGramPW * 4;
+  struct Col {
+    const unsigned char *p;  // 4-byte aligned address of the word that holds (row 0, column i)
+    uint32_t stride;         // bytes per panel row
+    uint32_t sel;            // PRMT selector of the element inside its word
+    int32_t pan;             // panel of the column
+    int32_t item;            // the column itself
+  };
+  static __device__ __forceinline__ Col col(const GramView &g, int i) {
+    const uint32_t wlog = i < g.h32 ? 2u : (i < g.h16 ? 1u : 0u);
+    const size_t byte = (size_t)__ldg(g.pbase + (i >> 6)) + ((size_t)(i & 63) << wlog);
+    Col c;
+    c.p = g.base + (byte & ~size_t(3));
+    c.stride = (uint32_t)kGramPW << wlog;
+    const uint32_t b = (uint32_t)(byte & 3);
+    c.sel = wlog == 2 ? 0x3210u : (wlog == 1 ? (0x4400u | ((b + 1) << 4) | b) : (0x4440u | b));
+    c.pan = i >> 6;
+    c.item = i;
+    return c;
+  }
+  static __device__ __forceinline__ bool stored(const GramView &g, int k, int pan_i) { return k < g.hd || (k >> 6) <= pan_i; }
+  static __device__ __forceinline__ uint32_t word(const unsigned char *p, uint32_t stride, int r) {
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"((uint32_t)r), "r"(stride), "l"(p));
+    return __ldg(reinterpret_cast<const uint32_t *>(a));
+  }
+  // G[ck.item][ci.item] from two column descriptors
+  static __device__ __forceinline__ double at(const GramView &g, const Col &ck, const Col &ci) {
+    const bool d = stored(g, ck.item, ci.pan);
+    const uint32_t w = d ? word(ci.p, ci.stride, ck.item) : word(ck.p, ck.stride, ci.item);
+    return (double)__byte_perm(w, 0u, d ? ci.sel : ck.sel);
+  }
+  static __device__ __forceinline__ double at(const GramView &g, const Col &ci, int k) {
+    if (stored(g, k, ci.pan)) return (double)__byte_perm(word(ci.p, ci.stride, k), 0u, ci.sel);
+    const Col ck = col(g, k);
+    return (double)__byte_perm(word(ck.p, ck.stride, ci.item), 0u, ck.sel);
+  }
+  static __device__ __forceinline__ double at(const GramView &g, int k, int i) { return at(g, col(g, i), k); }
 };
 
 struct GramArgs {
@@ -189,6 +263,18 @@ struct GbPacked {
     uint32_t stride, wlog;
     const size_t byte = GaPacked::col_byte(g, i, stride, wlog) + (size_t)k * stride;
     const uint32_t inc = (uint32_t)(a * b);  // integer ratings: exact
+    atomicAdd(reinterpret_cast<uint32_t *>(const_cast<unsigned char *>(g.base) + (byte & ~size_t(3))),
+              inc << ((uint32_t)(byte & 3) * 8u));
+  }
+};
+
+// stair layout: pairs whose element is not stored are skipped (the mirrored pair is stored)
+struct GbStair {
+  static __device__ __forceinline__ void add(const GramView &g, int k, int i, float a, float b) {
+    if (!GaStair::stored(g, k, i >> 6)) return;
+    const uint32_t wlog = i < g.h32 ? 2u : (i < g.h16 ? 1u : 0u);
+    const size_t byte = (size_t)__ldg(g.pbase + (i >> 6)) + (size_t)k * ((size_t)kGramPW << wlog) + ((size_t)(i & 63) << wlog);
+    const uint32_t inc = (uint32_t)(a * b);
     atomicAdd(reinterpret_cast<uint32_t *>(const_cast<unsigned char *>(g.base) + (byte & ~size_t(3))),
               inc << ((uint32_t)(byte & 3) * 8u));
   }
@@ -308,43 +394,63 @@ __device__ __forceinline__ double gram_allsum(GramSmem<CS> &sm, double v, uint32
 // The (row, value) pairs of a 32-entry chunk are staged in this warp's slice of shared memory and read back as
 // broadcasts: per gathered element one LDS (row), one mad.wide, one LDG, one PRMT, one I2F, one LDS.64 (value) and
 // the DFMA.
-struct GatherStage {
-  int row[32];
-  double val[32];
-};
-
 template <typename GA, int UNR>
-__device__ __forceinline__ double gram_gather_sum(const typename GA::Col &col, const int32_t *sl_row,
+__device__ __forceinline__ double gram_gather_sum(const GramView &gv, const typename GA::Col &col, const int32_t *sl_row,
                                                   const double *sl_val, int len, int first_chunk, int chunk_stride,
-                                                  GatherStage &st) {
+                                                  typename GA::Stage &st) {
   const int lane = threadIdx.x & 31;
   double acc = 0.0;
   for (int c = first_chunk; c * 32 < len; c += chunk_stride) {
     const int e = c * 32 + lane;
     __syncwarp();
-    st.row[lane] = e < len ? sl_row[e] : 0;
+    const int k_mine = e < len ? sl_row[e] : 0;
+    st.row[lane] = k_mine;
     st.val[lane] = e < len ? sl_val[e] : 0.0;  // entries past the end contribute 0 * G[0][col]
+    if constexpr (GA::kStair) {
+      const typename GA::Col ck = GA::col(gv, k_mine);
+      st.kp[lane] = ck.p;
+      st.ks[lane] = make_uint2(ck.stride, ck.sel);
+    }
     __syncwarp();
     const int cnt = min(32, len - c * 32);
-    for (int i0 = 0; i0 < cnt; i0 += UNR) {
-      typename GA::Raw g[UNR];  // UNR independent gathered loads in flight per lane
+    if constexpr (GA::kStair) {
+      // per element: row k of the lane's column when that is stored, row `item` of column k otherwise
+      for (int i0 = 0; i0 < cnt; i0 += UNR) {
+        uint32_t g[UNR];
 #pragma unroll
-      for (int u = 0; u < UNR; u++) g[u] = GA::raw(col, st.row[i0 + u]);
+        for (int u = 0; u < UNR; u++) {
+          const int k = st.row[i0 + u];
+          const bool d = GA::stored(gv, k, col.pan);
+          g[u] = GA::word(d ? col.p : st.kp[i0 + u], d ? col.stride : st.ks[i0 + u].x, d ? k : col.item);
+        }
 #pragma unroll
-      for (int u = 0; u < UNR; u++) acc = fma(st.val[i0 + u], GA::cvt(col, g[u]), acc);
+        for (int u = 0; u < UNR; u++) {
+          const bool d = GA::stored(gv, st.row[i0 + u], col.pan);
+          acc = fma(st.val[i0 + u], (double)__byte_perm(g[u], 0u, d ? col.sel : st.ks[i0 + u].y), acc);
+        }
+      }
+    } else {
+      for (int i0 = 0; i0 < cnt; i0 += UNR) {
+        typename GA::Raw g[UNR];  // UNR independent gathered loads in flight per lane
+#pragma unroll
+        for (int u = 0; u < UNR; u++) g[u] = GA::raw(col, st.row[i0 + u]);
+#pragma unroll
+        for (int u = 0; u < UNR; u++) acc = fma(st.val[i0 + u], GA::cvt(col, g[u]), acc);
+      }
     }
   }
   return acc;
 }
 
-// UNR = gathered loads in flight per lane: 16 with 64 registers (4 CTAs per SM) or 32 with 80 registers (3 CTAs per SM)
+// UNR = gathered loads in flight per lane: 16 with 64 registers (4 CTAs per SM) or 32 with 80 registers (3 CTAs per SM);
+// the stair accessor needs 80 registers at UNR = 16
 template <typename GA, int CS, int UNR>
-__global__ void __launch_bounds__(kGramNT, UNR > 16 ? 3 : 4) cd_gram_kernel(const SolveArgs a, const GramArgs ga) {
+__global__ void __launch_bounds__(kGramNT, (UNR > 16 || GA::kStair) ? 3 : 4) cd_gram_kernel(const SolveArgs a, const GramArgs ga) {
   constexpr int NT = kGramNT, NW = kGramNW;
   using Tile = typename GA::Tile;
   __shared__ GramSmem<CS> sm;
   __shared__ Tile s_gbb[32][33];
-  __shared__ GatherStage s_stage[NW];
+  __shared__ typename GA::Stage s_stage[NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = CS > 1 ? gram_cluster_rank() : 0u;
@@ -384,7 +490,11 @@ __global__ void __launch_bounds__(kGramNT, UNR > 16 ? 3 : 4) cd_gram_kernel(cons
     if (q >= ga.q_end) break;
     const int j = a.targets[q];
     const int cntj = a.colcnt[j];
-    auto gj_at = [&](int i) { return GA::at(gv, j, i); };  // aTy_i = G[j][i]
+    const typename GA::Col colj = GA::col(gv, j);
+    auto gj_at = [&](int i) {  // aTy_i = G[j][i]
+      if constexpr (GA::kStair) return GA::at(gv, colj, GA::col(gv, i));
+      else return GA::at(gv, j, i);
+    };
     const bool timer = rank == 0 && tid == 0;
     unsigned long long t_start = 0, t_act = 0, t_sweep = 0;
     if (timer) t_start = globaltimer_ns();
@@ -492,17 +602,17 @@ __global__ void __launch_bounds__(kGramNT, UNR > 16 ? 3 : 4) cd_gram_kernel(cons
             const double cn = (double)__ldg(a.cnorms + ab);
             den = 1.0 / (cn * cn + a.l2r);  // reciprocal of cnorm^2 + l2r (cd.c:127), taken off the chain's critical path
             sq = __ldg(a.csq + ab);
-            aty = (double)(float)GA::at(cab, j);  // G[j][ab]; gk_fkv_t.key is a float (estimate.c:437)
+            aty = (double)(float)GA::at(gv, cab, j);  // G[j][ab]; gk_fkv_t.key is a float (estimate.c:437)
           }
           // in-block Gram rows: warp w stages rows 4w .. 4w+3
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             const int r = warp * 4 + u;
-            if (p0 + r < na) s_gbb[r][lane] = (Tile)GA::at(cab, act[p0 + r]);
+            if (p0 + r < na) s_gbb[r][lane] = (Tile)GA::at(gv, cab, act[p0 + r]);
           }
           // <a_m, yhat> for the 32 coordinates of the block: this warp's share of the sum over S
           const int len = sm.len;
-          sm.part[warp][lane] = gram_gather_sum<GA, UNR>(cab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW, s_stage[warp]);
+          sm.part[warp][lane] = gram_gather_sum<GA, UNR>(gv, cab, sl_row, sl_val, len, (int)rank * NW + warp, CS * NW, s_stage[warp]);
           __syncthreads();
           if (warp == 0) {
             double ipf = 0.0;
@@ -582,7 +692,7 @@ __global__ void __launch_bounds__(kGramNT, UNR > 16 ? 3 : 4) cd_gram_kernel(cons
         const int e = cb * 32 + lane;
         const int col = sl_row[e < len ? e : 0];
         const double vk = e < len ? sl_val[e] : 0.0;
-        const double s = gram_gather_sum<GA, UNR>(GA::col(gv, col), sl_row, sl_val, len, warp, NW, s_stage[warp]);
+        const double s = gram_gather_sum<GA, UNR>(gv, GA::col(gv, col), sl_row, sl_val, len, warp, NW, s_stage[warp]);
         hh = fma(vk, s, hh);
       }
     }

@@ -34,7 +34,7 @@ def test_exports_every_declared_symbol(lib):
     from slim_b200 import _lib
 
     declared = _declared()
-    assert len(declared) == 45
+    assert len(declared) == 46
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None

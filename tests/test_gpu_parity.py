@@ -443,6 +443,95 @@ def test_gram_medium_matrix_cluster_class(lib, oracle, monkeypatch):
     assert np.allclose(stats["objval"], ref["stats"]["objval"], rtol=1e-9)
 
 
+# ---- STAIR layout of G (gram.cuh: GaStair): the layout when the full N x N matrix does not fit (BASELINE configs[4]) ----
+
+@pytest.mark.parametrize("hd", ["64", "256", "1000000"])
+def test_gram_stair_layout_is_exact(lib, monkeypatch, hd):
+    # panel p keeps rows [0, max(64 (p + 1), hd)); every element read back through the mirror rule == R^T R
+    import scipy.sparse as sp
+
+    from slim_b200 import Staged
+
+    monkeypatch.setenv("SLIMB200_GRAM_LAYOUT", "stair")
+    monkeypatch.setenv("SLIMB200_GRAM_HD", hd)
+    for ratings, nu, ni, per in ((False, 3000, 200, 25), (True, 9000, 1200, 12)):
+        rp, ri, rv = st.synth_zipf(nu, ni, per, seed=8, ratings=ratings)
+        R = sp.csr_matrix((rv.astype(np.float64), ri, rp), shape=(nu, ni))
+        G = (R.T @ R).toarray()
+        with Staged(rp, ri, rv) as s:
+            got = s.gram()
+            rank = s.item_order()
+            nbytes, h32, h16 = s.gram_layout()
+            stair, hdv = s.gram_stair()
+        ld = (ni + 127) // 128 * 128
+        assert stair == 1 and hdv == min((int(hd) + 63) // 64 * 64, ld)
+        inv = np.argsort(rank)
+        assert np.array_equal(got.astype(np.float64), G[np.ix_(inv, inv)])
+        pan = np.arange(ld // 64)
+        rows = np.minimum(ni, np.maximum((pan + 1) * 64, hdv))
+        width = np.where(pan * 64 < h32, 4, np.where(pan * 64 < h16, 2, 1))
+        assert nbytes == int((rows * 64 * width).sum()) + 16
+
+
+@pytest.mark.parametrize("hd", ["64", "256"])
+@pytest.mark.parametrize("route", ["single", "cluster", "user", "mixed"])
+def test_gram_stair_kernels(lib, oracle, monkeypatch, hd, route):
+    # one-target Gram kernels on the stair layout (direct and mirrored elements, all three widths); "user": every
+    # target above the giant threshold goes to the user-space cluster kernel in the same call; "mixed": both
+    monkeypatch.setenv("SLIMB200_GRAM_LAYOUT", "stair")
+    monkeypatch.setenv("SLIMB200_GRAM_HD", hd)
+    monkeypatch.setenv("SLIMB200_GRAM_HEAVY", "0" if route == "cluster" else ("60" if route == "mixed" else "1000000000"))
+    monkeypatch.setenv("SLIMB200_STAIR_USER", {"single": "1000000000", "cluster": "1000000000", "user": "0",
+                                               "mixed": "150"}[route])
+    from slim_b200 import Staged, learn_columns
+
+    rp, ri, rv = st.synth_zipf(9000, 1200, 12, seed=8, ratings=True)
+    cols = np.arange(0, 1200, 5, dtype=np.int32)
+    with Staged(rp, ri, rv) as s:
+        assert s.gram_stair()[0] == 1
+        r = learn_columns(s, dict(niters=40), cols=cols)
+        got, stats = r.to_host(), r.stats()
+    ref = oracle.learn(rp, ri, rv, niters=40, cols=cols, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
+    assert np.array_equal(stats["nactive"], ref["stats"]["nactive"])
+    assert np.array_equal(stats["niters"], ref["stats"]["niters"])
+    _check_close(got, ref, tol=1e-6)
+    assert np.allclose(stats["objval"], ref["stats"]["objval"], rtol=1e-9)
+
+
+def test_gram_stair_full_model_golden(lib, ours, monkeypatch):
+    # SLIM_Learn on the stair layout with giants in user space == the reference golden (ml100k, converged)
+    monkeypatch.setenv("SLIMB200_GRAM_LAYOUT", "stair")
+    monkeypatch.setenv("SLIMB200_GRAM_HD", "128")
+    monkeypatch.setenv("SLIMB200_STAIR_USER", "250")
+    g = st.load_golden("ml100k")
+    h = _learn(ours, g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], l1r=1.0, l2r=1.0, **CONV)
+    _check_close(st.model_views(h), _golden_model(g, "conv"))
+    ours.free(h)
+
+
+def test_gram_stair_warm_start_and_fslim(lib, ours, oracle, monkeypatch):
+    monkeypatch.setenv("SLIMB200_GRAM_LAYOUT", "stair")
+    monkeypatch.setenv("SLIMB200_GRAM_HD", "64")
+    monkeypatch.setenv("SLIMB200_STAIR_USER", "120")
+    rp, ri, rv = st.synth_zipf(900, 200, 20, seed=17, ratings=True)
+    h0 = _learn(ours, rp, ri, rv, l1r=3.0, l2r=1.0, niters=30)
+    m0 = st.model_views(h0)
+    h1 = _learn(ours, rp, ri, rv, imodel=h0, l1r=1.0, l2r=1.0, niters=5)
+    w1 = oracle.learn(rp, ri, rv, l1r=1.0, l2r=1.0, niters=5, nthreads=4,
+                      imodel=(m0["ncols"], m0["colptr"], m0["colind"], m0["colval"]), order=st.ORDER_POPULARITY)
+    _check_close(st.model_views(h1), w1, tol=1e-6)
+    for h in (h0, h1):
+        ours.free(h)
+    # fSLIM on the stair layout: the reference's golden model (neighbour sets incl. boundary ties)
+    g, f = st.load_golden("ml100k"), st.load_golden("fslim")
+    io, do = st.options(l1r=1.0, l2r=1.0, nnbrs=int(f["nnbrs"]), simtype="cos", **CONV)
+    h, status = ours.learn(g["trn_rowptr"], g["trn_rowind"], g["trn_rowval"], io, do)
+    assert h and status == st.SLIM_OK
+    ref = dict(colptr=f["ml100k_cos_colptr"], colind=f["ml100k_cos_colind"], colval=f["ml100k_cos_colval"])
+    _check_close(st.model_views(h), ref)
+    ours.free(h)
+
+
 # ---- batched heavy-target kernel (slim_b200/csrc/gram_batch.cuh): 8 targets per cluster, item-space blocks ----
 
 @pytest.mark.parametrize("bcs", ["1", "4", "8", "16"])
