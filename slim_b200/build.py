@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libslim.so"
 SOURCES = [CSRC / "engine.cu", CSRC / "api.cpp"]
-HEADERS = [CSRC / "engine.h", CSRC / "gram.cuh", CSRC / "gram_batch.cuh", CSRC / "predict.cuh", CSRC / "gather.cuh", CSRC / "fslim.cuh", PKG.parent / "include" / "slim.h", PKG.parent / "include" / "slim_b200.h"]
+HEADERS = [CSRC / "engine.h", CSRC / "gram.cuh", CSRC / "gram_batch.cuh", CSRC / "hybrid.cuh", CSRC / "predict.cuh", CSRC / "gather.cuh", CSRC / "fslim.cuh", PKG.parent / "include" / "slim.h", PKG.parent / "include" / "slim_b200.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--split-compile", "0",

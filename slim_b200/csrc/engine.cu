@@ -2492,6 +2492,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
 
 #include "gram.cuh"
 #include "gram_batch.cuh"
+#include "hybrid.cuh"
 #include "fslim.cuh"
 #include "predict.cuh"
 
@@ -2915,6 +2916,42 @@ static int gram_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &
   throw EngineError(kErr, "gram_launch: unsupported cluster size");
 }
 
+// cd_hybrid_kernel (hybrid.cuh): one cluster of `cs` CTAs x 512 threads per giant target; query = co-resident clusters
+template <typename GA, bool HV>
+static int hybrid_launch_t(const SolveArgs &args, const HybridArgs &hargs, int cs, int count, cudaStream_t s, bool query_only) {
+  auto kern = cd_hybrid_kernel<GA, HV>;
+  const size_t dyn = sizeof(HybSmem);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  if (cs > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)(cs * std::max(count, 1)), 1, 1);
+  cfg.blockDim = dim3(kHybNT, 1, 1);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (query_only) {
+    int n = 0;
+    CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    return n;
+  }
+  CK(cudaLaunchKernelEx(&cfg, kern, args, hargs));
+  return 0;
+}
+
+static int hybrid_launch(bool stair, bool vals, const SolveArgs &args, const HybridArgs &hargs, int cs, int count,
+                         cudaStream_t s, bool query_only) {
+  if (stair) return vals ? hybrid_launch_t<GaStair, true>(args, hargs, cs, count, s, query_only)
+                         : hybrid_launch_t<GaStair, false>(args, hargs, cs, count, s, query_only);
+  return vals ? hybrid_launch_t<GaPacked, true>(args, hargs, cs, count, s, query_only)
+              : hybrid_launch_t<GaPacked, false>(args, hargs, cs, count, s, query_only);
+}
+
 constexpr int kBatchT = 8, kBatchV = 2;
 
 template <typename GA, int CS, int NTB>
@@ -3048,38 +3085,51 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     // yhat too large for shared memory: thread-block clusters with yhat resident in L2
     int cs = env_int("SLIMB200_CLUSTER", plan.ysmem ? 0 : 16);
     if (cs != 0 && cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) cs = 16;
-    // STAIR layout of G (build_gram): the one-target Gram kernels solve every target below SLIMB200_STAIR_USER
-    // nonzeros; the giants above it (their sweeps would gather |S| x |A| ~ 10^10 elements, more than the nnz(R) a
-    // user-space sweep streams) go to the user-space cluster kernel, launched side by side with the Gram classes
+    // GIANT targets next to a resident packed Gram matrix: in the STAIR layout (build_gram) a Gram-space sweep of a
+    // target with >= ~5 000 nonzeros gathers |S| x |A| ~ 10^9 scattered elements, more than the nnz(R) entries a
+    // user-space sweep streams, so those targets go to cd_hybrid_kernel (hybrid.cuh: user-space inner products, exact
+    // block solve with Gram tiles), launched side by side with the Gram classes.  SLIMB200_STAIR_USER sets the
+    // threshold for the stair layout, SLIMB200_HYBRID_MIN for any packed layout (default: never for the full layout,
+    // where the batched kernel is faster); SLIMB200_GIANT_KERNEL=cluster runs them on cd_cluster_kernel instead.
     const bool stair = use_gram && m->gram_stair;
-    const int stair_user = (stair && !fslim) ? env_int("SLIMB200_STAIR_USER", 30000) : INT32_MAX;
+    const int stair_user = (use_gram && !m->gram_f64 && !fslim)
+                               ? env_int("SLIMB200_HYBRID_MIN", stair ? env_int("SLIMB200_STAIR_USER", 5000) : INT32_MAX)
+                               : INT32_MAX;
     int32_t n_user = 0;
-    if (stair)
+    if (stair_user != INT32_MAX)
       for (int32_t q = 0; q < nsel; q++) n_user += m->h_colcnt[m->h_rank[colof(q)]] >= stair_user ? 1 : 0;
     const bool mixed = n_user > 0;
+    const char *gk = getenv("SLIMB200_GIANT_KERNEL");
+    const bool giant_hybrid = mixed && !(gk && !strcmp(gk, "cluster"));
     if (mixed && cs == 0) cs = 16;
+    if (giant_hybrid) {
+      cs = env_int("SLIMB200_HYBRID_CS", 16);
+      if (cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) cs = 16;
+    }
     if (use_gram && !mixed) cs = 0;
     const bool use_cluster = cs > 0;
     const bool use_window = use_cluster && env_int("SLIMB200_WINDOW", 1) != 0;
     const size_t col_stride = use_gram ? m->gram_ld : (((size_t)std::max(ncols, 1) + 3) & ~size_t(3));
     const size_t row_stride = ((size_t)std::max(nrows, 1) + 3) & ~size_t(3);
     int nclusters = 0;
+    HybridArgs hargs{};
     if (use_cluster) {
-      int hw = cluster_dispatch(kernel_vals, use_window, args, cargs, cs, 1, s, true);
+      int hw = giant_hybrid ? hybrid_launch(stair, kernel_vals, args, hargs, cs, 1, s, true)
+                            : cluster_dispatch(kernel_vals, use_window, args, cargs, cs, 1, s, true);
       if (hw < 1) throw EngineError(kErr, "learn: cluster launch configuration not supported on this device");
       // keep the yhat vectors of all clusters in flight inside L2 (default budget 96 MB of 126 MB)
       const size_t l2_budget = (size_t)env_int("SLIMB200_L2_MB", 96) << 20;
       const int by_l2 = (int)std::max<size_t>(1, l2_budget / (row_stride * sizeof(double)));
       // ... but never fewer than 8 clusters: with very many users (C5: 40 MB per yhat) part of the gathers
       // then comes from HBM, which still beats leaving most SMs idle
-      nclusters = std::min(hw, std::max(by_l2, 8));
+      nclusters = giant_hybrid ? hw : std::min(hw, std::max(by_l2, 8));
       if (env_int("SLIMB200_NCLUSTERS", 0) > 0) nclusters = env_int("SLIMB200_NCLUSTERS", 0);
       nclusters = std::max(1, std::min(std::min(nclusters, hw), std::max(mixed ? n_user : nsel, 1)));
       plan.grid = nclusters * cs;
       if (env_int("SLIMB200_VERBOSE", 0))
-        fprintf(stderr, "[slim-b200] cluster kernel: cluster=%d CTAs x %d threads, %d clusters in flight (hw max %d, "
-                        "L2 budget allows %d), values=%d, window sweep=%d\n", cs, kClusterNT, nclusters, hw, by_l2,
-                (int)kernel_vals, (int)use_window);
+        fprintf(stderr, "[slim-b200] %s: cluster=%d CTAs x %d threads, %d clusters in flight (hw max %d, "
+                        "L2 budget allows %d), values=%d, window sweep=%d\n", giant_hybrid ? "hybrid kernel" : "cluster kernel",
+                cs, giant_hybrid ? kHybNT : kClusterNT, nclusters, hw, by_l2, (int)kernel_vals, (int)use_window);
     }
     const int user_grid = use_cluster ? nclusters * cs : 0;  // CTAs of the user-space cluster launch
     if (!use_cluster && !use_gram) {
@@ -3175,8 +3225,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       }
       plan.grid = std::max(1, slots);
       if (mixed && env_int("SLIMB200_VERBOSE", 0))
-        fprintf(stderr, "[slim-b200] stair layout: %d targets with nnz >= %d -> user-space cd_cluster_kernel\n", n_user,
-                stair_user);
+        fprintf(stderr, "[slim-b200] %d giant targets with nnz >= %d -> %s\n", n_user, stair_user,
+                giant_hybrid ? "cd_hybrid_kernel" : "cd_cluster_kernel");
     }
 
     // ---- scratch (cached on the matrix) --------------------------------------------------------
@@ -3271,10 +3321,15 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     cargs.nonneg = m->nonneg ? 1 : 0;
     cargs.groups = reinterpret_cast<GroupMeta *>(sb + o_grp);
     cargs.grp_stride = grp_stride;
+    hargs.colsplit = m->d_colsplit;
+    hargs.rows_per_part = m->rows_per_part;
+    hargs.xc = reinterpret_cast<double *>(sb + o_x);
+    hargs.expand = m->d_expand;
     args.act_idx = reinterpret_cast<int32_t *>(sb + o_idx);
     if (use_gram) {
       gargs.gv = GramView{static_cast<const unsigned char *>(m->d_gram), (size_t)ncols, m->gram_h32, m->gram_h16,
                           m->gram_off16, m->gram_off8, stair ? m->d_gram_pbase : nullptr, stair ? m->gram_hd : 0};
+      hargs.gv = gargs.gv;
       gargs.act = reinterpret_cast<int32_t *>(sb + o_idx) + gu * col_stride;
       gargs.x = reinterpret_cast<double *>(sb + o_x) + gux * col_stride;
       gargs.slotp = reinterpret_cast<int32_t *>(sb + o_gslot);
@@ -3421,13 +3476,15 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
           };
           int32_t q_next = 0;
           if (mixed) {
-            // stair layout: the giants at the head of the list go to the user-space cluster kernel
+            // the giants at the head of the list go to cd_hybrid_kernel (or the user-space cluster kernel)
             while (q_next < nt && m->h_colcnt[tcols[q_next]] >= stair_user) q_next++;
             if (q_next > 0) {
               SolveArgs ua = args;
               ua.ntargets = q_next;
               ua.queue = d_queue.p + 7;
-              cluster_dispatch(kernel_vals, use_window, ua, cargs, cs, std::min(nclusters, (int)q_next), next_stream(), false);
+              const int ncl = std::min(nclusters, (int)q_next);
+              if (giant_hybrid) hybrid_launch(stair, kernel_vals, ua, hargs, cs, ncl, next_stream(), false);
+              else cluster_dispatch(kernel_vals, use_window, ua, cargs, cs, ncl, next_stream(), false);
             }
           }
           // the Gram kernels index their scratch slots from the end of the user-space slots

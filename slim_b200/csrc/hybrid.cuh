@@ -1,0 +1,570 @@
+// hybrid.cuh -- the GIANT targets of a matrix whose Gram matrix is resident; included by engine.cu.
+//
+// A giant target (tens of thousands of users, an active set of 10^5 coordinates and a nonzero set S of a third of
+// that) is expensive in both formulations: a Gram-space sweep gathers |S| x |A| ~ 10^9-10^10 elements of G, a
+// user-space sweep streams nnz(active columns) ~ nnz(R) entries -- fewer, but cd_cluster_kernel spends a fixed
+// ~12 us per 32-ITEM window on its exchange / solve chain, 15 625 windows per sweep for 500 K items.
+// This kernel takes what is cheap from each side:
+//   * <a_i, yhat> comes from user space (reference cd.c:122-123): one pass over the columns of a block of
+//     kHybBK = 128 consecutive ACTIVE coordinates against the yhat at the start of the round; CTA r of the cluster
+//     owns user range r (colsplit) and with it a private slice of yhat;
+//   * the sequential dependence inside the block (cd.c:117-133 visits the coordinates one after the other) is
+//     resolved exactly with the 128 x 128 Gram tile G[block][block] -- 16 K gathered elements of the resident G, read
+//     ahead while the previous block's chain runs -- by one warp that only visits coordinates whose value changes;
+//   * yhat += d_i a_i (cd.c:129) for the coordinates that changed, fp64 reductions into the CTA's own slice.
+// A round costs one cluster barrier per 128 active coordinates; inactive items cost nothing.  Iterates, stop rule,
+// cap and compaction are those of the other kernels (estimate.c:433-505).
+#pragma once
+
+constexpr int kHybNT = 512;
+constexpr int kHybNW = kHybNT / 32;
+constexpr int kHybBK = 128;
+constexpr int kHybLane = 16;    // entries of a column inside the CTA's user range: one LANE takes the column
+constexpr int kHybGroup = 128;  // ... 8 lanes
+constexpr int kHybWarp = 8192;  // ... one warp; longer ranges are split over all warps of the CTA
+
+struct HybridArgs {
+  GramView gv;
+  const int32_t *colsplit;  // [ncols][kParts + 1]
+  int32_t rows_per_part;
+  double *xc;               // per CTA [col_stride]: every CTA keeps its own copy of x (identical values)
+  const unsigned long long *expand;
+};
+
+struct __align__(16) HybMeta {  // one block of active coordinates, as seen by this CTA
+  long long c0[kHybBK];     // padded offset of the column
+  double inv_den[kHybBK];   // 1 / (cnorm^2 + l2r)
+  double sq[kHybBK];        // exact sum of squares
+  int s0[kHybBK], s1[kHybBK];  // this CTA's entry range inside the column
+  float aty[kHybBK];
+  unsigned char cls[kHybBK];  // 0: empty range, 1: lane, 2: group of 8 lanes, 3: warp, 4: whole CTA
+  unsigned bmask[4];          // class-4 columns
+  unsigned wmask[4];          // class-3 columns
+  unsigned gmask[4];          // class-2 columns
+};
+
+struct __align__(16) HybSmem {
+  float tile[2][kHybBK][kHybBK];  // G[block][block] (upper triangle used), double buffered
+  HybMeta meta[2];
+  double mine[2][kHybBK];         // this CTA's partial inner products; peers read them through DSMEM
+  double pwb[kHybNW][kHybBK];     // per-warp partials of the class-4 columns
+  double tot[kHybBK];             // cluster-wide sums
+  double dlt[kHybBK];             // yhat step per coordinate
+  double red[kHybNW];
+  int sc[kHybNW];
+  int q, na, done;
+  double dl;
+  long long off;
+};
+
+__device__ __forceinline__ void hyb_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double hyb_ld_peer(const double *local, uint32_t peer) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(peer));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ void hyb_st_peer_int(int *local, uint32_t peer, int v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(peer));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+
+// entries e_k = e0 + sub + G k, k < 16, of column range [.., s1): 16 id loads, then 16 yhat gathers in flight per lane
+template <bool HASVAL, int G>
+__device__ __forceinline__ double hyb_dot16(const SolveArgs &a, long long c0, int e0, int s1, int sub, const double *yh) {
+  const int32_t *ix = a.colind + c0;
+  int id[16];
+  float vl[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int e = e0 + sub + G * k;
+    id[k] = e < s1 ? __ldg(ix + e) : -1;
+    if (HASVAL) vl[k] = e < s1 ? __ldg(a.colval + c0 + e) : 0.f;
+  }
+  double y[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) y[k] = __ldcg(yh + (id[k] < 0 ? 0 : id[k]));
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) acc += id[k] < 0 ? 0.0 : (HASVAL ? (double)vl[k] * y[k] : y[k]);
+  return acc;
+}
+
+template <bool HASVAL, int G>
+__device__ __forceinline__ void hyb_axpy16(const SolveArgs &a, long long c0, int e0, int s1, int sub, double d, double *yh) {
+  const int32_t *ix = a.colind + c0;
+  int id[16];
+  float vl[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int e = e0 + sub + G * k;
+    id[k] = e < s1 ? __ldg(ix + e) : -1;
+    if (HASVAL) vl[k] = e < s1 ? __ldg(a.colval + c0 + e) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 16; k++)
+    if (id[k] >= 0) atomicAdd(yh + id[k], HASVAL ? d * (double)vl[k] : d);
+}
+
+template <typename GA, bool HASVAL>
+__global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a, const HybridArgs ha) {
+  constexpr int NT = kHybNT, NW = kHybNW, BK = kHybBK;
+  extern __shared__ __align__(128) unsigned char hyb_dyn[];
+  HybSmem &sm = *reinterpret_cast<HybSmem *>(hyb_dyn);
+  cg::cluster_group cl = cg::this_cluster();
+  const int cs = (int)cl.num_blocks();
+  const uint32_t rank = cl.block_rank();
+  const int cid = blockIdx.x / cs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const GramView &gv = ha.gv;
+
+  const int pr0 = (int)rank * (kParts / cs), pr1 = ((int)rank + 1) * (kParts / cs);
+  const int64_t ulo64 = (int64_t)pr0 * ha.rows_per_part, uhi64 = (int64_t)pr1 * ha.rows_per_part;
+  const int u_lo = (int)(ulo64 < a.nrows ? ulo64 : a.nrows), u_hi = (int)(uhi64 < a.nrows ? uhi64 : a.nrows);
+
+  float *xw = a.xw + (size_t)cid * a.col_stride;
+  int32_t *act = a.act_idx + (size_t)cid * a.col_stride;
+  double *x = ha.xc + (size_t)blockIdx.x * a.col_stride;
+  double *yh = a.yhat + (size_t)cid * a.row_stride;
+  unsigned xb = 0;  // exchange buffer of the next round (kernel lifetime)
+  hyb_cluster_sync();  // every CTA of the cluster has started: its shared memory may be written from now on
+
+  for (;;) {
+    // ---- next target -------------------------------------------------------------------------------
+    if (rank == 0 && tid == 0) {
+      const int q = atomicAdd(a.queue, 1);
+      for (int c = 0; c < cs; c++) hyb_st_peer_int(&sm.q, (uint32_t)c, q);
+    }
+    hyb_cluster_sync();
+    const int q = sm.q;
+    if (q >= a.ntargets) break;
+    const int j = a.targets[q];
+    const int cntj = a.colcnt[j];
+    const typename GA::Col colj = GA::col(gv, j);
+    auto gj_at = [&](int i) {  // aTy_i = G[j][i]
+      if constexpr (GA::kStair) return GA::at(gv, colj, GA::col(gv, i));
+      else return GA::at(gv, j, i);
+    };
+    const bool timer = rank == 0 && tid == 0;
+    unsigned long long t_start = 0, t_act = 0, t_sweep = 0;
+    if (timer) t_start = globaltimer_ns();
+
+    // ---- warm start (estimate.c:455-458) and active set (estimate.c:433-444), built by CTA 0 ---------
+    const int jo = a.inv[j];
+    const bool warm = a.wcolptr != nullptr && jo < a.wncols;
+    long long actnnz = 0;
+    if (rank == 0) {
+      if (warm) {
+        for (int64_t k = a.wcolptr[jo] + tid; k < a.wcolptr[jo + 1]; k += NT) {
+          const int r = a.wcolind[k];
+          if (r >= 0 && r < a.ncols) xw[a.rank[r]] = a.wcolval[k];
+        }
+      }
+      int na = 0;
+      for (int base = 0; base < a.ncols; base += NT) {
+        const int i = base + tid;
+        double v = 0.0;
+        if (i < a.ncols) v = gj_at(i);
+        const bool flag = (i < a.ncols) && (i != j) && (v > a.l1r);
+        int tot;
+        const int pos = na + team_excl_scan<NT>(flag, sm.sc, tot);
+        if (flag) {
+          act[pos] = i;
+          actnnz += a.colcnt[i];
+        }
+        na += tot;
+      }
+      if (tid == 0)
+        for (int c = 0; c < cs; c++) hyb_st_peer_int(&sm.na, (uint32_t)c, na);
+    }
+    __threadfence();
+    hyb_cluster_sync();
+    const int na = sm.na;
+    for (int p = tid; p < na; p += NT) x[p] = warm ? (double)__ldcg(&xw[__ldcg(&act[p])]) : 0.0;
+    __syncthreads();
+    hyb_cluster_sync();  // every CTA has read xw before CTA 0 clears it
+    if (warm && rank == 0) {
+      for (int64_t k = a.wcolptr[jo] + tid; k < a.wcolptr[jo + 1]; k += NT) {
+        const int r = a.wcolind[k];
+        if (r >= 0 && r < a.ncols) xw[a.rank[r]] = 0.0f;
+      }
+    }
+    const long long cap64 = 50LL * cntj;
+    const int maxit = (int)(cap64 < (long long)a.maxniters ? cap64 : (long long)a.maxniters);
+    const int nblk = (na + BK - 1) / BK;
+
+    // metadata and Gram tile of block `b` into buffer `nb`; called by the warps 1 .. NW-1 (warp 0 runs the chain)
+    auto prefetch = [&](int b, int nb) {
+      if (warp == 0) return;
+      HybMeta &M = sm.meta[nb];
+      const int p0 = b * BK;
+      const int n = min(BK, na - p0);
+      if (warp >= 1 && warp <= 4) {
+        const int m = tid - 32;
+        int cls = 0;
+        if (m < n) {
+          const int i = __ldcg(&act[p0 + m]);
+          const int32_t *sp = ha.colsplit + (size_t)i * (kParts + 1);
+          const int s0 = __ldg(sp + pr0), s1 = __ldg(sp + pr1);
+          M.c0[m] = __ldg(a.colptr + i);
+          M.s0[m] = s0;
+          M.s1[m] = s1;
+          const double cn = (double)__ldg(a.cnorms + i);
+          M.inv_den[m] = 1.0 / (cn * cn + a.l2r);
+          M.sq[m] = __ldg(a.csq + i);
+          M.aty[m] = (float)gj_at(i);  // gk_fkv_t.key is a float (estimate.c:437)
+          const int len = s1 - s0;
+          cls = len <= 0 ? 0 : (len <= kHybLane ? 1 : (len <= kHybGroup ? 2 : (len <= kHybWarp ? 3 : 4)));
+        }
+        if (m < BK) M.cls[m] = (unsigned char)cls;
+        const unsigned b4 = __ballot_sync(0xffffffffu, cls == 4), b3 = __ballot_sync(0xffffffffu, cls == 3);
+        const unsigned b2 = __ballot_sync(0xffffffffu, cls == 2);
+        if (lane == 0) {
+          M.bmask[warp - 1] = b4;
+          M.wmask[warp - 1] = b3;
+          M.gmask[warp - 1] = b2;
+        }
+      }
+      // tile rows r = warp-1, warp-1 + (NW-1), ...; lane takes the columns lane + 32 c4 (upper triangle only)
+      int ci[4];
+      typename GA::Col cc[4];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; c4++) {
+        const int c = lane + 32 * c4;
+        ci[c4] = c < n ? __ldcg(&act[p0 + c]) : -1;
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < 4; c4++) cc[c4] = GA::col(gv, ci[c4] < 0 ? 0 : ci[c4]);
+      for (int r = warp - 1; r < n; r += NW - 1) {
+        const int k = __ldcg(&act[p0 + r]);
+        typename GA::Col ck = cc[0];
+        if constexpr (GA::kStair) ck = GA::col(gv, k);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+          const int c = lane + 32 * c4;
+          if (c > r && c < n) {
+            double v;
+            if constexpr (GA::kStair) v = GA::at(gv, ck, cc[c4]);
+            else v = GA::at(gv, cc[c4], k);
+            sm.tile[nb][r][c] = (float)v;
+          }
+        }
+      }
+    };
+
+    // yhat slice += d * (this CTA's range of the block's columns), for the coordinates with d != 0
+    auto update_yhat = [&](const HybMeta &M, int n) {
+      if (tid < n && M.cls[tid] == 1) {  // one lane per column
+        const double d = sm.dlt[tid];
+        if (d != 0.0) hyb_axpy16<HASVAL, 1>(a, M.c0[tid], M.s0[tid], M.s1[tid], 0, d, yh);
+      }
+      if ((M.gmask[0] | M.gmask[1] | M.gmask[2] | M.gmask[3]) != 0u) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int m = (tid >> 3) + 64 * h;
+          if (m < n && M.cls[m] == 2) {
+            const double d = sm.dlt[m];
+            if (d != 0.0) hyb_axpy16<HASVAL, 8>(a, M.c0[m], M.s0[m], M.s1[m], lane & 7, d, yh);
+          }
+        }
+      }
+      if ((M.wmask[0] | M.wmask[1] | M.wmask[2] | M.wmask[3]) != 0u) {
+        for (int m = warp; m < n; m += NW)
+          if (M.cls[m] == 3) {
+            const double d = sm.dlt[m];
+            if (d != 0.0)
+              for (int e0 = M.s0[m]; e0 < M.s1[m]; e0 += 512) hyb_axpy16<HASVAL, 32>(a, M.c0[m], e0, M.s1[m], lane, d, yh);
+          }
+      }
+#pragma unroll
+      for (int w4 = 0; w4 < 4; w4++) {
+        unsigned mm = M.bmask[w4];
+        while (mm) {
+          const int m = 32 * w4 + __ffs(mm) - 1;
+          mm &= mm - 1;
+          const double d = sm.dlt[m];
+          if (d != 0.0)
+            for (int e0 = M.s0[m] + warp * 512; e0 < M.s1[m]; e0 += NW * 512)
+              hyb_axpy16<HASVAL, 32>(a, M.c0[m], e0, M.s1[m], lane, d, yh);
+        }
+      }
+    };
+
+    int cur = 0;
+    if (nblk > 0) prefetch(0, cur);
+    __syncthreads();
+
+    // ---- warm start: yhat slice = sum_k x_k a_k over this CTA's user range -------------------------------
+    if (warm && nblk > 0) {
+      for (int b = 0; b < nblk; b++) {
+        const int p0 = b * BK, n = min(BK, na - p0);
+        if (tid < BK) {
+          const double xi = tid < n ? x[p0 + tid] : 0.0;
+          sm.dlt[tid] = fabs(xi) > kEps ? xi : 0.0;
+        }
+        __syncthreads();
+        update_yhat(sm.meta[cur], n);
+        if (warp >= 1) prefetch(b + 1 == nblk ? 0 : b + 1, cur ^ 1);
+        __threadfence();
+        __syncthreads();
+        cur ^= 1;
+      }
+    }
+
+    // ---- the sweeps (cd.c:112-140) ---------------------------------------------------------------------
+    if (timer) t_act = globaltimer_ns();
+    int niters = 1;
+    if (na > 0 && maxit > 0) {
+      bool done = false;
+      int t = 0;
+      for (; t < maxit && !done; t++) {
+        double dl = 0.0;  // warp 0: this lane's share of sum (x' - x)^2
+        for (int b = 0; b < nblk; b++) {
+          const HybMeta &M = sm.meta[cur];
+          const int p0 = b * BK, n = min(BK, na - p0);
+          double xv[4] = {0.0, 0.0, 0.0, 0.0};
+          if (warp == 0) {
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+              if (32 * s + lane < n) xv[s] = x[p0 + 32 * s + lane];
+          }
+          // ---- partial inner products <a_m, yhat> over this CTA's user range
+          if (tid < n && M.cls[tid] <= 1)
+            sm.mine[xb][tid] = M.cls[tid] == 1 ? hyb_dot16<HASVAL, 1>(a, M.c0[tid], M.s0[tid], M.s1[tid], 0, yh) : 0.0;
+          if ((M.gmask[0] | M.gmask[1] | M.gmask[2] | M.gmask[3]) != 0u) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int m = (tid >> 3) + 64 * h;
+              const bool on = m < n && M.cls[m] == 2;
+              double v = on ? hyb_dot16<HASVAL, 8>(a, M.c0[m], M.s0[m], M.s1[m], lane & 7, yh) : 0.0;
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              v += __shfl_xor_sync(0xffffffffu, v, 2);
+              v += __shfl_xor_sync(0xffffffffu, v, 4);
+              if (on && (lane & 7) == 0) sm.mine[xb][m] = v;
+            }
+          }
+          if ((M.wmask[0] | M.wmask[1] | M.wmask[2] | M.wmask[3]) != 0u) {
+            for (int m = warp; m < n; m += NW)
+              if (M.cls[m] == 3) {
+                double v = 0.0;
+                for (int e0 = M.s0[m]; e0 < M.s1[m]; e0 += 512) v += hyb_dot16<HASVAL, 32>(a, M.c0[m], e0, M.s1[m], lane, yh);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) sm.mine[xb][m] = v;
+              }
+          }
+          const bool anybig = (M.bmask[0] | M.bmask[1] | M.bmask[2] | M.bmask[3]) != 0u;
+          if (anybig) {
+#pragma unroll
+            for (int w4 = 0; w4 < 4; w4++) {
+              unsigned mm = M.bmask[w4];
+              while (mm) {
+                const int m = 32 * w4 + __ffs(mm) - 1;
+                mm &= mm - 1;
+                double v = 0.0;
+                for (int e0 = M.s0[m] + warp * 512; e0 < M.s1[m]; e0 += NW * 512)
+                  v += hyb_dot16<HASVAL, 32>(a, M.c0[m], e0, M.s1[m], lane, yh);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) sm.pwb[warp][m] = v;
+              }
+            }
+            __syncthreads();
+            if (tid < n && M.cls[tid] == 4) {
+              double s = 0.0;
+#pragma unroll
+              for (int w = 0; w < NW; w++) s += sm.pwb[w][tid];
+              sm.mine[xb][tid] = s;
+            }
+          }
+          // ---- sum over the CTAs of the cluster (rank order: bit-identical everywhere)
+          hyb_cluster_sync();
+          if (tid < n) {
+            double s = 0.0;
+            for (int c = 0; c < cs; c++) s += hyb_ld_peer(&sm.mine[xb][tid], (uint32_t)c);
+            sm.tot[tid] = s;
+          }
+          xb ^= 1u;
+          __syncthreads();
+
+          if (warp == 0) {
+            // ---- exact sequential CD inside the block (cd.c:117-133); only coordinates whose value changes are visited
+            const float(*T)[BK] = sm.tile[cur];
+            double ipf[4], xn[4], sq[4], den[4], aty[4];
+            bool valid[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+              const int m = 32 * s + lane;
+              valid[s] = m < n;
+              ipf[s] = valid[s] ? sm.tot[m] : 0.0;
+              sq[s] = valid[s] ? M.sq[m] : 0.0;
+              den[s] = valid[s] ? M.inv_den[m] : 1.0;
+              aty[s] = valid[s] ? (double)M.aty[m] : 0.0;
+              xn[s] = xv[s];
+            }
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+              if (32 * s >= n) break;
+              int k = 0;
+              for (;;) {
+                const double in_old = fabs(xn[s]) > kEps ? xn[s] : 0.0;
+                const double ip = ipf[s] - in_old * sq[s];  // cd.c:122-123 in one step
+                const double num = aty[s] - ip;
+                const double nx = num > a.l1r ? (num - a.l1r) * den[s] : 0.0;
+                const unsigned want = __ballot_sync(0xffffffffu, valid[s] && lane >= k && nx != xn[s]);
+                if (!want) break;
+                const int kk = __ffs(want) - 1;
+                const double in_new = fabs(nx) > kEps ? nx : 0.0;
+                const double d = __shfl_sync(0xffffffffu, in_new - in_old, kk);
+                if (lane == kk) {
+                  dl += (nx - xn[s]) * (nx - xn[s]);
+                  xn[s] = nx;
+                }
+                if (d != 0.0) {
+                  const float *row = T[32 * s + kk];
+#pragma unroll
+                  for (int s2 = 0; s2 < 4; s2++)
+                    if (s2 >= s) ipf[s2] = fma(d, (double)row[32 * s2 + lane], ipf[s2]);
+                }
+                k = kk + 1;
+              }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+              const int m = 32 * s + lane;
+              const double was = fabs(xv[s]) > kEps ? xv[s] : 0.0;
+              const double now = fabs(xn[s]) > kEps ? xn[s] : 0.0;
+              if (valid[s] && xn[s] != xv[s]) x[p0 + m] = xn[s];
+              sm.dlt[m] = valid[s] ? now - was : 0.0;
+            }
+          } else {
+            prefetch(b + 1 == nblk ? 0 : b + 1, cur ^ 1);
+          }
+          __syncthreads();
+          update_yhat(M, n);
+          __threadfence();
+          __syncthreads();
+          cur ^= 1;
+        }
+        // ---- end of sweep: stop rule (cd.c:135-138)
+        if (warp == 0) {
+#pragma unroll
+          for (int o = 16; o; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o);
+          if (lane == 0) sm.done = dl < a.opttol ? 1 : 0;
+        }
+        __syncthreads();
+        done = sm.done != 0;
+        __syncthreads();
+      }
+      niters = done ? t : maxit + 1;  // cd.c:140
+    } else if (maxit > 0) {
+      niters = (0.0 < a.opttol) ? 1 : maxit + 1;
+    }
+    if (timer) t_sweep = globaltimer_ns();
+
+    // ---- residual (estimate.c:477-489): |y - yhat|^2 = sum_u yhat_u^2 + sum_{u in col j} (r_uj^2 - 2 r_uj yhat_u);
+    //      the pass over the slice also clears it for the next target
+    double jdot = 0.0, ssq = 0.0;
+    {
+      const int32_t *sp = ha.colsplit + (size_t)j * (kParts + 1);
+      const int s0 = sp[pr0], s1 = sp[pr1];
+      const int64_t cj0 = a.colptr[j];
+      for (int e = s0 + tid; e < s1; e += NT) {
+        const double r = HASVAL ? (double)a.colval[cj0 + e] : 1.0;
+        jdot = fma(r, __ldcg(yh + a.colind[cj0 + e]), jdot);
+      }
+      __syncthreads();
+      for (int u = u_lo + tid; u < u_hi; u += NT) {
+        const double v = __ldcg(yh + u);
+        if (v != 0.0) {
+          ssq = fma(v, v, ssq);
+          __stcg(yh + u, 0.0);
+        }
+      }
+    }
+    auto cta_sum = [&](double v) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      __syncthreads();
+      if (lane == 0) sm.red[warp] = v;
+      __syncthreads();
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) s += sm.red[w];
+      return s;
+    };
+    jdot = cta_sum(jdot);
+    ssq = cta_sum(ssq);
+    if (tid == 0) {
+      sm.mine[xb][0] = jdot;
+      sm.mine[xb][1] = ssq;
+    }
+    __threadfence();
+    hyb_cluster_sync();
+    double jd_all = 0.0, ss_all = 0.0;
+    if (rank == 0)
+      for (int c = 0; c < cs; c++) {
+        jd_all += hyb_ld_peer(&sm.mine[xb][0], (uint32_t)c);
+        ss_all += hyb_ld_peer(&sm.mine[xb][1], (uint32_t)c);
+      }
+    xb ^= 1u;
+
+    if (rank == 0) {
+      double reg = 0.0;
+      int nnz_local = 0;
+      for (int p = tid; p < na; p += NT) {
+        const double xv = x[p];
+        reg += 0.5 * a.l2r * xv * xv + a.l1r * fabs(xv);
+        nnz_local += fabs(xv) > kEps ? 1 : 0;
+      }
+      reg = cta_sum(reg);
+      const int nnz_w = (int)(cta_sum((double)nnz_local) + 0.5);
+      const double actnnz_t = cta_sum((double)actnnz);
+      // ---- compaction |x| > EPS -> (i, (float)x) in visiting order (estimate.c:492-505)
+      if (tid == 0) sm.off = (long long)atomicAdd(a.pool_used, (unsigned long long)nnz_w);
+      __syncthreads();
+      const long long off = sm.off;
+      const bool fits = off + nnz_w <= a.pool_cap;
+      if (fits) {
+        int w0 = 0;
+        for (int base = 0; base < na; base += NT) {
+          const int p = base + tid;
+          double xv = 0.0;
+          if (p < na) xv = x[p];
+          const bool flag = (p < na) && fabs(xv) > kEps;
+          int tot;
+          const int pos = w0 + team_excl_scan<NT>(flag, sm.sc, tot);
+          if (flag) {
+            a.pool_idx[off + pos] = a.inv[act[p]];
+            a.pool_val[off + pos] = (float)xv;
+          }
+          w0 += tot;
+        }
+      }
+      if (tid == 0) {
+        a.out_cnt[q] = fits ? nnz_w : -1 - nnz_w;
+        a.out_off[q] = off;
+        a.st_niters[q] = niters;
+        a.st_nactive[q] = na;
+        a.st_actnnz[q] = (long long)(actnnz_t + 0.5);
+        a.st_expand[q] = ha.expand ? (long long)ha.expand[j] : 0;
+        const double rn = 0.5 * (ss_all - 2.0 * jd_all + a.csq[j]);
+        a.st_rnorm[q] = rn;
+        a.st_obj[q] = rn + reg;
+        a.st_ngroups[q] = nblk;
+        const unsigned long long t_end = globaltimer_ns();
+        a.st_phase[(size_t)q * 4 + 0] = 0.f;
+        a.st_phase[(size_t)q * 4 + 1] = (float)(t_act - t_start) * 1e-3f;
+        a.st_phase[(size_t)q * 4 + 2] = (float)(t_sweep - t_act) * 1e-3f;
+        a.st_phase[(size_t)q * 4 + 3] = (float)(t_end - t_sweep) * 1e-3f;
+      }
+    }
+    __threadfence();
+  }
+  // no CTA may exit while a peer can still read its shared memory
+  hyb_cluster_sync();
+}

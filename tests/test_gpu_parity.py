@@ -474,10 +474,14 @@ def test_gram_stair_layout_is_exact(lib, monkeypatch, hd):
 
 
 @pytest.mark.parametrize("hd", ["64", "256"])
-@pytest.mark.parametrize("route", ["single", "cluster", "user", "mixed"])
+@pytest.mark.parametrize("route", ["single", "cluster", "user", "mixed", "user-cluster", "mixed-cluster"])
 def test_gram_stair_kernels(lib, oracle, monkeypatch, hd, route):
     # one-target Gram kernels on the stair layout (direct and mirrored elements, all three widths); "user": every
-    # target above the giant threshold goes to the user-space cluster kernel in the same call; "mixed": both
+    # target above the giant threshold goes to cd_hybrid_kernel in the same call ("-cluster": to the user-space
+    # cd_cluster_kernel); "mixed": both
+    if route.endswith("-cluster"):
+        monkeypatch.setenv("SLIMB200_GIANT_KERNEL", "cluster")
+        route = route[:-8]
     monkeypatch.setenv("SLIMB200_GRAM_LAYOUT", "stair")
     monkeypatch.setenv("SLIMB200_GRAM_HD", hd)
     monkeypatch.setenv("SLIMB200_GRAM_HEAVY", "0" if route == "cluster" else ("60" if route == "mixed" else "1000000000"))
@@ -530,6 +534,66 @@ def test_gram_stair_warm_start_and_fslim(lib, ours, oracle, monkeypatch):
     ref = dict(colptr=f["ml100k_cos_colptr"], colind=f["ml100k_cos_colind"], colval=f["ml100k_cos_colval"])
     _check_close(st.model_views(h), ref)
     ours.free(h)
+
+
+# ---- giant targets next to a resident Gram matrix (slim_b200/csrc/hybrid.cuh): user-space inner products, Gram tiles ----
+
+@pytest.mark.parametrize("layout", ["stair", "full"])
+@pytest.mark.parametrize("cs", ["1", "4", "8", "16"])
+@pytest.mark.parametrize("ratings,null_vals", [(False, False), (True, False), (False, True)])
+def test_hybrid_kernel_variants(lib, ours, oracle, monkeypatch, layout, cs, ratings, null_vals):
+    monkeypatch.setenv("SLIMB200_GRAM_LAYOUT", layout)
+    monkeypatch.setenv("SLIMB200_GRAM_HD", "64")
+    monkeypatch.setenv("SLIMB200_HYBRID_MIN", "0")  # every target
+    monkeypatch.setenv("SLIMB200_HYBRID_CS", cs)
+    rp, ri, rv = st.synth_zipf(1000, 260, 24, seed=29, ratings=ratings)
+    if null_vals:
+        rv = None
+    kw = dict(l1r=0.7, l2r=1.5, **CONV)
+    h = _learn(ours, rp, ri, rv, **kw)
+    w = oracle.learn(rp, ri, rv, nthreads=8, **kw, order=st.ORDER_POPULARITY)
+    _check_close(st.model_views(h), w)
+    ours.free(h)
+
+
+@pytest.mark.parametrize("cs,hmin", [("1", "0"), ("2", "0"), ("16", "0"), ("16", "2000")])
+def test_hybrid_long_columns_and_iteration_cap(lib, oracle, monkeypatch, cs, hmin):
+    # 40 000 users: column ranges of every class (one lane, 8 lanes, one warp, the whole CTA), several blocks of 128
+    # active coordinates, capped head targets that must follow the oracle sweep by sweep; "2000": the lighter targets
+    # run on the Gram kernels in the same call
+    monkeypatch.setenv("SLIMB200_GRAM_LAYOUT", "stair")
+    monkeypatch.setenv("SLIMB200_GRAM_HD", "128")
+    monkeypatch.setenv("SLIMB200_HYBRID_MIN", hmin)
+    monkeypatch.setenv("SLIMB200_HYBRID_CS", cs)
+    from slim_b200 import Staged, learn_columns
+
+    rp, ri, rv = st.synth_zipf(40000, 600, 30, seed=77)
+    cols = np.arange(0, 600, 13, dtype=np.int32)
+    with Staged(rp, ri, rv) as s:
+        r = learn_columns(s, dict(niters=30), cols=cols)
+        got, stats = r.to_host(), r.stats()
+    ref = oracle.learn(rp, ri, rv, niters=30, cols=cols, nthreads=8, want_stats=True, order=st.ORDER_POPULARITY)
+    assert np.array_equal(stats["nactive"], ref["stats"]["nactive"])
+    assert np.array_equal(stats["active_nnz"], ref["stats"]["active_nnz"])
+    assert np.array_equal(stats["niters"], ref["stats"]["niters"])
+    _check_close(got, ref, tol=1e-6)
+    assert np.allclose(stats["objval"], ref["stats"]["objval"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(stats["rnorm"], ref["stats"]["rnorm"], rtol=1e-9, atol=1e-7)
+
+
+@pytest.mark.parametrize("cs", ["1", "16"])
+def test_hybrid_warm_start_and_real_ratings(lib, ours, oracle, monkeypatch, cs):
+    monkeypatch.setenv("SLIMB200_HYBRID_MIN", "0")
+    monkeypatch.setenv("SLIMB200_HYBRID_CS", cs)
+    rp, ri, rv = st.synth_zipf(900, 200, 20, seed=17, ratings=True)
+    h0 = _learn(ours, rp, ri, rv, l1r=3.0, l2r=1.0, niters=30)
+    m0 = st.model_views(h0)
+    h1 = _learn(ours, rp, ri, rv, imodel=h0, l1r=1.0, l2r=1.0, niters=5)
+    w1 = oracle.learn(rp, ri, rv, l1r=1.0, l2r=1.0, niters=5, nthreads=4,
+                      imodel=(m0["ncols"], m0["colptr"], m0["colind"], m0["colval"]), order=st.ORDER_POPULARITY)
+    _check_close(st.model_views(h1), w1, tol=1e-6)
+    for h in (h0, h1):
+        ours.free(h)
 
 
 # ---- batched heavy-target kernel (slim_b200/csrc/gram_batch.cuh): 8 targets per cluster, item-space blocks ----
