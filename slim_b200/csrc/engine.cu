@@ -2493,6 +2493,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
 #include "gram.cuh"
 #include "gram_batch.cuh"
 #include "hybrid.cuh"
+static_assert(sizeof(HybLine) == sizeof(ActMetaC), "cd_hybrid_kernel reuses the scratch of cd_cluster_kernel's lines");
 #include "fslim.cuh"
 #include "predict.cuh"
 
@@ -2920,7 +2921,7 @@ static int gram_launch(bool f64, int cs, const SolveArgs &args, const GramArgs &
 template <typename GA, bool HV>
 static int hybrid_launch_t(const SolveArgs &args, const HybridArgs &hargs, int cs, int count, cudaStream_t s, bool query_only) {
   auto kern = cd_hybrid_kernel<GA, HV>;
-  const size_t dyn = sizeof(HybSmem);
+  const size_t dyn = sizeof(HybSmem<GA, HV>);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   if (cs > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
@@ -3324,6 +3325,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     hargs.colsplit = m->d_colsplit;
     hargs.rows_per_part = m->rows_per_part;
     hargs.xc = reinterpret_cast<double *>(sb + o_x);
+    hargs.lines = reinterpret_cast<HybLine *>(sb + o_meta);  // (the slot of cd_cluster_kernel's ActMetaC lines: same size)
     hargs.expand = m->d_expand;
     args.act_idx = reinterpret_cast<int32_t *>(sb + o_idx);
     if (use_gram) {
@@ -3383,7 +3385,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         DevBuf<double> d_rn, d_ob;
         DevBuf<float> d_ph;
         DevBuf<int32_t> d_ng;
-        DevBuf<unsigned long long> d_used;
+        DevBuf<unsigned long long> d_used, d_hprof;
+        int32_t n_hprof = 0;
         d_targets.alloc(nt);
         d_queue.alloc_zero(8, s);
         d_used.alloc_zero(1, s);
@@ -3475,6 +3478,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
             return st;
           };
           int32_t q_next = 0;
+          hargs.prof = nullptr;
           if (mixed) {
             // the giants at the head of the list go to cd_hybrid_kernel (or the user-space cluster kernel)
             while (q_next < nt && m->h_colcnt[tcols[q_next]] >= stair_user) q_next++;
@@ -3483,6 +3487,11 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
               ua.ntargets = q_next;
               ua.queue = d_queue.p + 7;
               const int ncl = std::min(nclusters, (int)q_next);
+              if (giant_hybrid && env_int("SLIMB200_PROFILE", 0)) {
+                d_hprof.alloc_zero((size_t)q_next * 10, s);
+                hargs.prof = d_hprof.p;
+                n_hprof = q_next;
+              }
               if (giant_hybrid) hybrid_launch(stair, kernel_vals, ua, hargs, cs, ncl, next_stream(), false);
               else cluster_dispatch(kernel_vals, use_window, ua, cargs, cs, ncl, next_stream(), false);
             }
@@ -3542,6 +3551,19 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         CK(cudaMemcpyAsync(h_rn.data(), d_rn.p, sizeof(double) * nt, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(h_ob.data(), d_ob.p, sizeof(double) * nt, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        if (n_hprof > 0) {  // SLIMB200_PROFILE=1: cycle split of the hybrid kernel's rounds, per giant target
+          std::vector<unsigned long long> hp((size_t)n_hprof * 10);
+          CK(cudaMemcpy(hp.data(), d_hprof.p, sizeof(unsigned long long) * hp.size(), cudaMemcpyDeviceToHost));
+          for (int32_t k = 0; k < n_hprof; k++) {
+            const unsigned long long *pp = &hp[(size_t)k * 10];
+            fprintf(stderr, "[slim-b200] hybrid target %d (nnz %d): short rounds %llu: dots %.2f xchg %.2f chain %.2f upd %.2f us "
+                            "each | long rounds %llu: dots %.1f xchg %.1f chain %.1f upd %.1f us each (at 1.9 GHz)\n",
+                    k, m->h_colcnt[tcols[k]], pp[8], pp[0] / 1.9e3 / std::max<double>(pp[8], 1), pp[1] / 1.9e3 / std::max<double>(pp[8], 1),
+                    pp[2] / 1.9e3 / std::max<double>(pp[8], 1), pp[3] / 1.9e3 / std::max<double>(pp[8], 1), pp[9],
+                    pp[4] / 1.9e3 / std::max<double>(pp[9], 1), pp[5] / 1.9e3 / std::max<double>(pp[9], 1),
+                    pp[6] / 1.9e3 / std::max<double>(pp[9], 1), pp[7] / 1.9e3 / std::max<double>(pp[9], 1));
+          }
+        }
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, e0, e1));
         solve_ms += ms;

@@ -23,18 +23,40 @@ constexpr int kHybLane = 16;    // entries of a column inside the CTA's user ran
 constexpr int kHybGroup = 128;  // ... 8 lanes
 constexpr int kHybWarp = 8192;  // ... one warp; longer ranges are split over all warps of the CTA
 
+// One active coordinate of the current target, built once per target by the whole cluster (one 128-byte line):
+// a round's read-ahead is then ONE load latency instead of a chain act -> colptr / colsplit / pbase -> G.
+struct __align__(128) HybLine {
+  long long c0;               // padded offset of the column
+  double inv_den;             // 1 / (cnorm^2 + l2r)
+  double sq;                  // exact sum of squares
+  const unsigned char *gp;    // Gram column descriptor (GA::Col): word address of (row 0, column item) ...
+  uint32_t gstride, gsel;     // ... row stride and PRMT selector
+  float aty;                  // (float)G[j][item]: gk_fkv_t.key is a float (estimate.c:437)
+  int32_t item;
+  int32_t split[kParts + 1];  // entry offsets of the 16 user ranges inside the column
+  int32_t pad[3];
+};
+static_assert(sizeof(HybLine) == 128, "one line per active coordinate");
+
 struct HybridArgs {
   GramView gv;
   const int32_t *colsplit;  // [ncols][kParts + 1]
   int32_t rows_per_part;
   double *xc;               // per CTA [col_stride]: every CTA keeps its own copy of x (identical values)
+  HybLine *lines;           // per cluster [col_stride]
   const unsigned long long *expand;
+  // SLIMB200_PROFILE=1: per target 10 counters (clock64 cycles of CTA 0's thread 0): inner products / exchange /
+  // chain + read-ahead / yhat update, for rounds without and with long column ranges, and the two round counts
+  unsigned long long *prof;
 };
 
+template <typename GA>
 struct __align__(16) HybMeta {  // one block of active coordinates, as seen by this CTA
-  long long c0[kHybBK];     // padded offset of the column
-  double inv_den[kHybBK];   // 1 / (cnorm^2 + l2r)
-  double sq[kHybBK];        // exact sum of squares
+  typename GA::Col dcol[kHybBK];  // where column act[p] of G lives (gathers of the tile need no dependent load)
+  int item[kHybBK];
+  long long c0[kHybBK];
+  double inv_den[kHybBK];
+  double sq[kHybBK];
   int s0[kHybBK], s1[kHybBK];  // this CTA's entry range inside the column
   float aty[kHybBK];
   unsigned char cls[kHybBK];  // 0: empty range, 1: lane, 2: group of 8 lanes, 3: warp, 4: whole CTA
@@ -43,14 +65,18 @@ struct __align__(16) HybMeta {  // one block of active coordinates, as seen by t
   unsigned gmask[4];          // class-2 columns
 };
 
+template <typename GA, bool HASVAL>
 struct __align__(16) HybSmem {
   float tile[2][kHybBK][kHybBK];  // G[block][block] (upper triangle used), double buffered
-  HybMeta meta[2];
+  HybMeta<GA> meta[2];
+  int sid[2][kHybLane][kHybBK];                                      // user ids of the class-1 columns, read ahead
+  float sval[HASVAL ? 2 : 1][HASVAL ? kHybLane : 1][HASVAL ? kHybBK : 1];  // ... and their values
   double mine[2][kHybBK];         // this CTA's partial inner products; peers read them through DSMEM
   double pwb[kHybNW][kHybBK];     // per-warp partials of the class-4 columns
   double tot[kHybBK];             // cluster-wide sums
   double dlt[kHybBK];             // yhat step per coordinate
   double red[kHybNW];
+  unsigned dep[2][4];             // coordinates of the block whose tile row has a nonzero above the diagonal ("emitters")
   int sc[kHybNW];
   int q, na, done;
   double dl;
@@ -71,6 +97,12 @@ __device__ __forceinline__ void hyb_st_peer_int(int *local, uint32_t peer, int v
   uint32_t ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(peer));
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+
+// fire-and-forget fp64 reduction (SASS REDG.E.ADD.F64): atomicAdd() with an unused result is compiled to a returning
+// ATOMG inside these loops, and a lane's next ATOMG waits for the previous one
+__device__ __forceinline__ void hyb_red_add(double *p, double v) {
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
 // entries e_k = e0 + sub + G k, k < 16, of column range [.., s1): 16 id loads, then 16 yhat gathers in flight per lane
@@ -107,14 +139,14 @@ __device__ __forceinline__ void hyb_axpy16(const SolveArgs &a, long long c0, int
   }
 #pragma unroll
   for (int k = 0; k < 16; k++)
-    if (id[k] >= 0) atomicAdd(yh + id[k], HASVAL ? d * (double)vl[k] : d);
+    if (id[k] >= 0) hyb_red_add(yh + id[k], HASVAL ? d * (double)vl[k] : d);
 }
 
 template <typename GA, bool HASVAL>
 __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a, const HybridArgs ha) {
   constexpr int NT = kHybNT, NW = kHybNW, BK = kHybBK;
   extern __shared__ __align__(128) unsigned char hyb_dyn[];
-  HybSmem &sm = *reinterpret_cast<HybSmem *>(hyb_dyn);
+  HybSmem<GA, HASVAL> &sm = *reinterpret_cast<HybSmem<GA, HASVAL> *>(hyb_dyn);
   cg::cluster_group cl = cg::this_cluster();
   const int cs = (int)cl.num_blocks();
   const uint32_t rank = cl.block_rank();
@@ -130,6 +162,7 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
   int32_t *act = a.act_idx + (size_t)cid * a.col_stride;
   double *x = ha.xc + (size_t)blockIdx.x * a.col_stride;
   double *yh = a.yhat + (size_t)cid * a.row_stride;
+  HybLine *lines = ha.lines + (size_t)cid * a.col_stride;
   unsigned xb = 0;  // exchange buffer of the next round (kernel lifetime)
   hyb_cluster_sync();  // every CTA of the cluster has started: its shared memory may be written from now on
 
@@ -185,8 +218,35 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
     hyb_cluster_sync();
     const int na = sm.na;
     for (int p = tid; p < na; p += NT) x[p] = warm ? (double)__ldcg(&xw[__ldcg(&act[p])]) : 0.0;
+    // one line per active coordinate, filled by all CTAs of the cluster
+    for (int p = (int)rank * NT + tid; p < na; p += cs * NT) {
+      const int i = __ldcg(&act[p]);
+      const typename GA::Col ci = GA::col(gv, i);
+      const long long c0 = __ldg(a.colptr + i);
+      const double cn = (double)__ldg(a.cnorms + i);
+      const double inv_den = 1.0 / (cn * cn + a.l2r);
+      const double sq = __ldg(a.csq + i);
+      double aty;
+      if constexpr (GA::kStair) aty = GA::at(gv, colj, ci);
+      else aty = GA::at(gv, ci, j);
+      const int32_t *sp = ha.colsplit + (size_t)i * (kParts + 1);
+      int sv[kParts + 1];
+#pragma unroll
+      for (int k = 0; k <= kParts; k++) sv[k] = __ldg(sp + k);
+      const unsigned long long gp = (unsigned long long)ci.p;
+      int4 *dst = reinterpret_cast<int4 *>(&lines[p]);  // field order of HybLine
+      __stcg(dst + 0, make_int4((int)(unsigned)c0, (int)(c0 >> 32), __double2loint(inv_den), __double2hiint(inv_den)));
+      __stcg(dst + 1, make_int4(__double2loint(sq), __double2hiint(sq), (int)(unsigned)gp, (int)(gp >> 32)));
+      __stcg(dst + 2, make_int4((int)ci.stride, (int)ci.sel, __float_as_int((float)aty), i));
+      __stcg(dst + 3, make_int4(sv[0], sv[1], sv[2], sv[3]));
+      __stcg(dst + 4, make_int4(sv[4], sv[5], sv[6], sv[7]));
+      __stcg(dst + 5, make_int4(sv[8], sv[9], sv[10], sv[11]));
+      __stcg(dst + 6, make_int4(sv[12], sv[13], sv[14], sv[15]));
+      __stcg(dst + 7, make_int4(sv[16], 0, 0, 0));
+    }
+    __threadfence();
     __syncthreads();
-    hyb_cluster_sync();  // every CTA has read xw before CTA 0 clears it
+    hyb_cluster_sync();  // every CTA has read xw before CTA 0 clears it; the lines are complete
     if (warm && rank == 0) {
       for (int64_t k = a.wcolptr[jo] + tid; k < a.wcolptr[jo + 1]; k += NT) {
         const int r = a.wcolind[k];
@@ -197,70 +257,127 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
     const int maxit = (int)(cap64 < (long long)a.maxniters ? cap64 : (long long)a.maxniters);
     const int nblk = (na + BK - 1) / BK;
 
-    // metadata and Gram tile of block `b` into buffer `nb`; called by the warps 1 .. NW-1 (warp 0 runs the chain)
-    auto prefetch = [&](int b, int nb) {
-      if (warp == 0) return;
-      HybMeta &M = sm.meta[nb];
+    // Read-ahead of block `b` into buffer `nb`, every part ONE load latency deep:
+    //   prefetch_meta (warps 4-7, at the start of the previous round, before their share of the inner products):
+    //     the block's coordinate lines;
+    //   prefetch_ids (warps 4-7) and prefetch_tile (warps 1-3, 8-15), while warp 0 runs the previous block's chain:
+    //     the user ids of the short (class-1) column ranges and G[block][block] through the descriptors in shared memory.
+    auto prefetch_meta = [&](int b, int nb) {
+      if (warp < 4 || warp > 7) return;
+      HybMeta<GA> &M = sm.meta[nb];
       const int p0 = b * BK;
       const int n = min(BK, na - p0);
-      if (warp >= 1 && warp <= 4) {
-        const int m = tid - 32;
-        int cls = 0;
-        if (m < n) {
-          const int i = __ldcg(&act[p0 + m]);
-          const int32_t *sp = ha.colsplit + (size_t)i * (kParts + 1);
-          const int s0 = __ldg(sp + pr0), s1 = __ldg(sp + pr1);
-          M.c0[m] = __ldg(a.colptr + i);
-          M.s0[m] = s0;
-          M.s1[m] = s1;
-          const double cn = (double)__ldg(a.cnorms + i);
-          M.inv_den[m] = 1.0 / (cn * cn + a.l2r);
-          M.sq[m] = __ldg(a.csq + i);
-          M.aty[m] = (float)gj_at(i);  // gk_fkv_t.key is a float (estimate.c:437)
-          const int len = s1 - s0;
-          cls = len <= 0 ? 0 : (len <= kHybLane ? 1 : (len <= kHybGroup ? 2 : (len <= kHybWarp ? 3 : 4)));
+      const int m = tid - 128;
+      int cls = 0;
+      if (m < n) {
+        const HybLine *L = &lines[p0 + m];
+        const int4 h0 = __ldcg(reinterpret_cast<const int4 *>(L));      // c0, inv_den
+        const int4 h1 = __ldcg(reinterpret_cast<const int4 *>(L) + 1);  // sq, gp
+        const int4 h2 = __ldcg(reinterpret_cast<const int4 *>(L) + 2);  // gstride, gsel, aty, item
+        const int s0 = __ldcg(&L->split[pr0]), s1 = __ldcg(&L->split[pr1]);
+        typename GA::Col dc;
+        dc.p = reinterpret_cast<const unsigned char *>(((unsigned long long)(unsigned)h1.w << 32) | (unsigned)h1.z);
+        dc.stride = (uint32_t)h2.x;
+        dc.sel = (uint32_t)h2.y;
+        if constexpr (GA::kStair) {
+          dc.pan = h2.w >> 6;
+          dc.item = h2.w;
         }
-        if (m < BK) M.cls[m] = (unsigned char)cls;
-        const unsigned b4 = __ballot_sync(0xffffffffu, cls == 4), b3 = __ballot_sync(0xffffffffu, cls == 3);
-        const unsigned b2 = __ballot_sync(0xffffffffu, cls == 2);
-        if (lane == 0) {
-          M.bmask[warp - 1] = b4;
-          M.wmask[warp - 1] = b3;
-          M.gmask[warp - 1] = b2;
+        M.dcol[m] = dc;
+        M.item[m] = h2.w;
+        M.c0[m] = (long long)(((unsigned long long)(unsigned)h0.y << 32) | (unsigned)h0.x);
+        M.inv_den[m] = __hiloint2double(h0.w, h0.z);
+        M.sq[m] = __hiloint2double(h1.y, h1.x);
+        M.aty[m] = __int_as_float(h2.z);
+        M.s0[m] = s0;
+        M.s1[m] = s1;
+        const int len = s1 - s0;
+        cls = len <= 0 ? 0 : (len <= kHybLane ? 1 : (len <= kHybGroup ? 2 : (len <= kHybWarp ? 3 : 4)));
+      }
+      M.cls[m] = (unsigned char)cls;
+      const unsigned b4 = __ballot_sync(0xffffffffu, cls == 4), b3 = __ballot_sync(0xffffffffu, cls == 3);
+      const unsigned b2 = __ballot_sync(0xffffffffu, cls == 2);
+      if (lane == 0) {
+        M.bmask[warp - 4] = b4;
+        M.wmask[warp - 4] = b3;
+        M.gmask[warp - 4] = b2;
+        sm.dep[nb][warp - 4] = 0u;
+      }
+    };
+    auto prefetch_ids = [&](int nb) {  // needs meta[nb]
+      if (warp < 4 || warp > 7) return;
+      const HybMeta<GA> &M = sm.meta[nb];
+      const int m = tid - 128;
+      if (M.cls[m] == 1) {
+        const long long c0 = M.c0[m];
+        const int s0 = M.s0[m], len = M.s1[m] - s0;
+        int id[kHybLane];
+        float vl[kHybLane];
+#pragma unroll
+        for (int k = 0; k < kHybLane; k++) {
+          id[k] = k < len ? __ldg(a.colind + c0 + s0 + k) : 0;
+          if (HASVAL) vl[k] = k < len ? __ldg(a.colval + c0 + s0 + k) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kHybLane; k++) {
+          sm.sid[nb][k][m] = id[k];
+          if (HASVAL) sm.sval[nb][k][m] = vl[k];
         }
       }
-      // tile rows r = warp-1, warp-1 + (NW-1), ...; lane takes the columns lane + 32 c4 (upper triangle only)
-      int ci[4];
-      typename GA::Col cc[4];
+    };
+    auto prefetch_tile = [&](int b, int nb) {  // needs meta[nb]
+      if (warp == 0 || (warp >= 4 && warp <= 7)) return;
+      const HybMeta<GA> &M = sm.meta[nb];
+      const int n = min(BK, na - b * BK);
+      // the 8128 elements above the diagonal, flattened: rows P and 127 - P together hold exactly 127 of them
+      constexpr int NTH = (NW - 5) * 32, PER = (BK * (BK - 1) / 2 + NTH - 1) / NTH;
+      const int t = (warp < 4 ? warp - 1 : warp - 5) * 32 + lane;
+      constexpr int HALF = PER / 2;
+      static_assert(PER % 2 == 0, "two batches");
+#pragma unroll 1
+      for (int k0 = 0; k0 < PER; k0 += HALF) {  // two batches of HALF independent gathers per lane
+        float v[HALF];
 #pragma unroll
-      for (int c4 = 0; c4 < 4; c4++) {
-        const int c = lane + 32 * c4;
-        ci[c4] = c < n ? __ldcg(&act[p0 + c]) : -1;
-      }
+        for (int k = 0; k < HALF; k++) {
+          const int e = t + (k0 + k) * NTH;
+          const int P = e / (BK - 1), o = e - P * (BK - 1);
+          const bool top = o < BK - 1 - P;
+          const int r = top ? P : BK - 1 - P;
+          const int c = top ? P + 1 + o : BK - P + (o - (BK - 1 - P));
+          double g = 0.0;
+          if (e < BK * (BK - 1) / 2 && c < n) {
+            if constexpr (GA::kStair) g = GA::at(gv, M.dcol[r], M.dcol[c]);
+            else g = GA::at(gv, M.dcol[c], M.item[r]);
+          }
+          v[k] = (float)g;
+        }
 #pragma unroll
-      for (int c4 = 0; c4 < 4; c4++) cc[c4] = GA::col(gv, ci[c4] < 0 ? 0 : ci[c4]);
-      for (int r = warp - 1; r < n; r += NW - 1) {
-        const int k = __ldcg(&act[p0 + r]);
-        typename GA::Col ck = cc[0];
-        if constexpr (GA::kStair) ck = GA::col(gv, k);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; c4++) {
-          const int c = lane + 32 * c4;
-          if (c > r && c < n) {
-            double v;
-            if constexpr (GA::kStair) v = GA::at(gv, ck, cc[c4]);
-            else v = GA::at(gv, cc[c4], k);
-            sm.tile[nb][r][c] = (float)v;
+        for (int k = 0; k < HALF; k++) {
+          const int e = t + (k0 + k) * NTH;
+          const int P = e / (BK - 1), o = e - P * (BK - 1);
+          const bool top = o < BK - 1 - P;
+          const int r = top ? P : BK - 1 - P;
+          const int c = top ? P + 1 + o : BK - P + (o - (BK - 1 - P));
+          if (e < BK * (BK - 1) / 2 && c < n) {
+            sm.tile[nb][r][c] = v[k];
+            if (v[k] != 0.f) atomicOr(&sm.dep[nb][r >> 5], 1u << (r & 31));
           }
         }
       }
     };
 
     // yhat slice += d * (this CTA's range of the block's columns), for the coordinates with d != 0
-    auto update_yhat = [&](const HybMeta &M, int n) {
-      if (tid < n && M.cls[tid] == 1) {  // one lane per column
-        const double d = sm.dlt[tid];
-        if (d != 0.0) hyb_axpy16<HASVAL, 1>(a, M.c0[tid], M.s0[tid], M.s1[tid], 0, d, yh);
+    auto update_yhat = [&](int buf, int n) {
+      const HybMeta<GA> &M = sm.meta[buf];
+      {  // class 1: user ids staged in shared memory, one entry per thread and pass (4 entries of every column per pass)
+        const int m = tid & (BK - 1);
+        if (m < n && M.cls[m] == 1) {
+          const double d = sm.dlt[m];
+          const int len = M.s1[m] - M.s0[m];
+          if (d != 0.0)
+            for (int k = tid >> 7; k < len; k += NT / BK)
+              hyb_red_add(yh + sm.sid[buf][k][m], HASVAL ? d * (double)sm.sval[HASVAL ? buf : 0][HASVAL ? k : 0][HASVAL ? m : 0] : d);
+        }
       }
       if ((M.gmask[0] | M.gmask[1] | M.gmask[2] | M.gmask[3]) != 0u) {
 #pragma unroll
@@ -295,25 +412,29 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
     };
 
     int cur = 0;
-    if (nblk > 0) prefetch(0, cur);
-    __syncthreads();
-
     // ---- warm start: yhat slice = sum_k x_k a_k over this CTA's user range -------------------------------
-    if (warm && nblk > 0) {
+    if (warm) {
       for (int b = 0; b < nblk; b++) {
         const int p0 = b * BK, n = min(BK, na - p0);
+        prefetch_meta(b, cur);
         if (tid < BK) {
           const double xi = tid < n ? x[p0 + tid] : 0.0;
           sm.dlt[tid] = fabs(xi) > kEps ? xi : 0.0;
         }
         __syncthreads();
-        update_yhat(sm.meta[cur], n);
-        if (warp >= 1) prefetch(b + 1 == nblk ? 0 : b + 1, cur ^ 1);
-        __threadfence();
+        prefetch_ids(cur);
         __syncthreads();
-        cur ^= 1;
+        update_yhat(cur, n);
+        __syncthreads();
       }
     }
+    if (nblk > 0) prefetch_meta(0, cur);
+    __syncthreads();
+    if (nblk > 0) {
+      prefetch_ids(cur);
+      prefetch_tile(0, cur);
+    }
+    __syncthreads();
 
     // ---- the sweeps (cd.c:112-140) ---------------------------------------------------------------------
     if (timer) t_act = globaltimer_ns();
@@ -324,8 +445,15 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
       for (; t < maxit && !done; t++) {
         double dl = 0.0;  // warp 0: this lane's share of sum (x' - x)^2
         for (int b = 0; b < nblk; b++) {
-          const HybMeta &M = sm.meta[cur];
+          const HybMeta<GA> &M = sm.meta[cur];
           const int p0 = b * BK, n = min(BK, na - p0);
+          const int bn = b + 1 == nblk ? 0 : b + 1;
+          const bool prof_on = ha.prof != nullptr && rank == 0 && tid == 0;
+          const int pheavy = ((M.bmask[0] | M.bmask[1] | M.bmask[2] | M.bmask[3] | M.wmask[0] | M.wmask[1] | M.wmask[2] |
+                               M.wmask[3]) != 0u) ? 4 : 0;
+          long long pt0 = 0, pt1 = 0, pt2 = 0, pt3 = 0;
+          if (prof_on) pt0 = clock64();
+          prefetch_meta(bn, cur ^ 1);
           double xv[4] = {0.0, 0.0, 0.0, 0.0};
           if (warp == 0) {
 #pragma unroll
@@ -333,8 +461,19 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
               if (32 * s + lane < n) xv[s] = x[p0 + 32 * s + lane];
           }
           // ---- partial inner products <a_m, yhat> over this CTA's user range
-          if (tid < n && M.cls[tid] <= 1)
-            sm.mine[xb][tid] = M.cls[tid] == 1 ? hyb_dot16<HASVAL, 1>(a, M.c0[tid], M.s0[tid], M.s1[tid], 0, yh) : 0.0;
+          if (tid < n && M.cls[tid] <= 1) {
+            double v = 0.0;
+            if (M.cls[tid] == 1) {  // user ids staged in shared memory: one load latency
+              const int len = M.s1[tid] - M.s0[tid];
+              double y[kHybLane];
+#pragma unroll
+              for (int k = 0; k < kHybLane; k++) y[k] = k < len ? __ldcg(yh + sm.sid[cur][k][tid]) : 0.0;
+#pragma unroll
+              for (int k = 0; k < kHybLane; k++)
+                v += HASVAL ? (double)sm.sval[HASVAL ? cur : 0][HASVAL ? k : 0][HASVAL ? tid : 0] * y[k] : y[k];
+            }
+            sm.mine[xb][tid] = v;
+          }
           if ((M.gmask[0] | M.gmask[1] | M.gmask[2] | M.gmask[3]) != 0u) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -382,6 +521,7 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
             }
           }
           // ---- sum over the CTAs of the cluster (rank order: bit-identical everywhere)
+          if (prof_on) pt1 = clock64();
           hyb_cluster_sync();
           if (tid < n) {
             double s = 0.0;
@@ -390,6 +530,7 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
           }
           xb ^= 1u;
           __syncthreads();
+          if (prof_on) pt2 = clock64();
 
           if (warp == 0) {
             // ---- exact sequential CD inside the block (cd.c:117-133); only coordinates whose value changes are visited
@@ -406,17 +547,28 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
               aty[s] = valid[s] ? (double)M.aty[m] : 0.0;
               xn[s] = xv[s];
             }
+            // Only a coordinate whose tile row has a nonzero after the diagonal ("emitter") can change a later inner
+            // product: the emitters that change are visited one after the other, every other coordinate of the
+            // sub-block takes its step in parallel afterwards (its ip then holds the steps of all earlier emitters,
+            // T is applied above the diagonal only).  Unpopular items rarely co-occur: few emitters per block.
 #pragma unroll
             for (int s = 0; s < 4; s++) {
               if (32 * s >= n) break;
+              const unsigned em = sm.dep[cur][s];
               int k = 0;
               for (;;) {
                 const double in_old = fabs(xn[s]) > kEps ? xn[s] : 0.0;
                 const double ip = ipf[s] - in_old * sq[s];  // cd.c:122-123 in one step
                 const double num = aty[s] - ip;
                 const double nx = num > a.l1r ? (num - a.l1r) * den[s] : 0.0;
-                const unsigned want = __ballot_sync(0xffffffffu, valid[s] && lane >= k && nx != xn[s]);
-                if (!want) break;
+                const unsigned want = __ballot_sync(0xffffffffu, valid[s] && lane >= k && nx != xn[s]) & em;
+                if (!want) {
+                  if (valid[s] && !((em >> lane) & 1u) && nx != xn[s]) {
+                    dl += (nx - xn[s]) * (nx - xn[s]);
+                    xn[s] = nx;
+                  }
+                  break;
+                }
                 const int kk = __ffs(want) - 1;
                 const double in_new = fabs(nx) > kEps ? nx : 0.0;
                 const double d = __shfl_sync(0xffffffffu, in_new - in_old, kk);
@@ -428,7 +580,7 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
                   const float *row = T[32 * s + kk];
 #pragma unroll
                   for (int s2 = 0; s2 < 4; s2++)
-                    if (s2 >= s) ipf[s2] = fma(d, (double)row[32 * s2 + lane], ipf[s2]);
+                    if (s2 > s || (s2 == s && lane > kk)) ipf[s2] = fma(d, (double)row[32 * s2 + lane], ipf[s2]);
                 }
                 k = kk + 1;
               }
@@ -442,12 +594,21 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
               sm.dlt[m] = valid[s] ? now - was : 0.0;
             }
           } else {
-            prefetch(b + 1 == nblk ? 0 : b + 1, cur ^ 1);
+            prefetch_ids(cur ^ 1);
+            prefetch_tile(bn, cur ^ 1);
           }
           __syncthreads();
-          update_yhat(M, n);
-          __threadfence();
-          __syncthreads();
+          if (prof_on) pt3 = clock64();
+          update_yhat(cur, n);
+          __syncthreads();  // (yhat slices are private to a CTA: block-level visibility is all the next round needs)
+          if (prof_on) {
+            unsigned long long *pp = ha.prof + (size_t)q * 10;
+            pp[pheavy + 0] += (unsigned long long)(pt1 - pt0);
+            pp[pheavy + 1] += (unsigned long long)(pt2 - pt1);
+            pp[pheavy + 2] += (unsigned long long)(pt3 - pt2);
+            pp[pheavy + 3] += (unsigned long long)(clock64() - pt3);
+            pp[8 + (pheavy >> 2)] += 1ull;
+          }
           cur ^= 1;
         }
         // ---- end of sweep: stop rule (cd.c:135-138)

@@ -16,12 +16,15 @@ nu, ni, pu = (int(v) for v in os.environ.get("PROBE_SHAPE", "5000000,500000,100"
 rp, ri, rv = zipf_csr(nu, ni, pu, device='cuda')
 colcnt = torch.bincount(ri.to(torch.int64), minlength=ni).cpu().numpy()
 cols = stratified_columns(colcnt, ncols_step, offset=1)
+all_cols = cols
 base = dict(os.environ)
 staged, staged_key = None, None
 for cfg in sys.argv[2:]:
     os.environ.clear(); os.environ.update(base)
     kv = {} if cfg == "default" else dict(x.split("=") for x in cfg.split(","))
     os.environ.update(kv)
+    lo_nnz = int(kv.get("PROBE_MIN_NNZ", "0"))  # only the step's targets with at least this many nonzeros
+    cols = all_cols[colcnt[all_cols] >= lo_nnz]
     key = tuple(sorted((k, v) for k, v in kv.items() if k in STAGE_KEYS))
     if staged is None or key != staged_key:
         if staged is not None:
@@ -32,7 +35,7 @@ for cfg in sys.argv[2:]:
     r = learn_columns(staged, dict(l1r=1.0, l2r=1.0, optTol=1e-7, niters=50), cols=cols)
     st, (ph, ng), w = r.stats(), r.phases(), r.to_host()
     wn = np.diff(w["colptr"])
-    print(cfg, "solve_ms %.1f" % r.solve_ms, "-> %.0f cols/s" % (ncols_step / r.solve_ms * 1e3), "nnz", r.nnz, flush=True)
+    print(cfg, "solve_ms %.1f" % r.solve_ms, "-> %.0f cols/s" % (len(cols) / r.solve_ms * 1e3), "nnz", r.nnz, flush=True)
     c = colcnt[cols]
     tot = ph.sum(1) * 1e-3
     for lo, hi in ((30000, 1 << 30), (9000, 30000), (5000, 9000), (2000, 5000), (500, 2000), (100, 500), (0, 100)):
