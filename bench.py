@@ -419,7 +419,7 @@ def main():
     gram_eb, gram_ms = staged.gram_info()
     gram_bytes, gram_h32, gram_h16 = staged.gram_layout()
     gram_stair, gram_hd = staged.gram_stair()
-    kernel_name = ("cd_gram_kernel on the stair-layout Gram matrix + cd_cluster_kernel for the giant targets "
+    kernel_name = ("cd_gram_kernel on the stair-layout Gram matrix + cd_hybrid_kernel for the giant targets "
                    "(concurrent launches)" if gram_stair else
                    "cd_gram_kernel + cd_gram_batch_kernel (Gram-space CD, concurrent launches)" if gram_eb
                    else "cd_cluster_kernel (user-space CD)")
