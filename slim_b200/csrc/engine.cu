@@ -134,6 +134,13 @@ __host__ __device__ __forceinline__ size_t gram_off(size_t nr, int k, int i) {
 }
 
 
+// Fire-and-forget fp64 reduction (SASS REDG.E.ADD.F64).  atomicAdd() with an unused result is compiled to a RETURNING
+// ATOMG inside the unrolled update loops of the user-space kernels, and a lane's next ATOMG then waits for the
+// previous one to come back from the L2 (profiles/r02_c5_hybrid_notes.txt).
+__device__ __forceinline__ void red_add_f64(double *p, double v) {
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // staged matrix
 // ------------------------------------------------------------------------------------------------
@@ -1081,7 +1088,7 @@ __global__ void __launch_bounds__(NT) cd_solve_kernel(const SolveArgs a) {
       for (int64_t k = r0 + lane; k < r1; k += 32) {
         const int i = __ldg(a.rowind + k);
         const double prod = HASVAL ? (double)__ldg(a.rowval + k) * vy : 1.0;
-        atomicAdd(&acc[i], prod);
+        red_add_f64(&acc[i], prod);
       }
       if (lane == 0) expand += (r1 - r0);
     }
@@ -1385,7 +1392,7 @@ template <bool HASVAL, bool L2 = false>
 __device__ __forceinline__ void axpy_chunk_r(const Chunk &r, int e0, int lo, int hi, double d, double *yh) {
 #define SLIM_UPD(i, v)                   \
   do {                                   \
-    if (L2) atomicAdd(yh + (i), (v));    \
+    if (L2) red_add_f64(yh + (i), (v));  \
     else yh[(i)] += (v);                 \
   } while (0)
   if (e0 + 0 >= lo && e0 + 0 < hi) SLIM_UPD(r.ix.x, HASVAL ? d * (double)r.vv.x : d);
@@ -1635,7 +1642,7 @@ __device__ __forceinline__ void warp_bigblock_axpy(const SolveArgs &a, int64_t c
   }
 #pragma unroll
   for (int k = 0; k < kBigPer; k++)
-    if (e + 32 * k >= s0 && e + 32 * k < s1) atomicAdd(yh + id[k], HASVAL ? d * (double)vl[k] : d);
+    if (e + 32 * k >= s0 && e + 32 * k < s1) red_add_f64(yh + id[k], HASVAL ? d * (double)vl[k] : d);
 }
 
 // Same over the whole CTA for LONG column ranges.  Entries are taken "transposed": one gather / atomic
@@ -1692,7 +1699,7 @@ __device__ __forceinline__ void block_axpy(const SolveArgs &a, int64_t c0, int s
       const int e = e0 + lane + 32 * k;
       if (e >= s0 && e < s1) {
         const int u = __ldg(ix + e);
-        atomicAdd(yh + u, HASVAL ? d * (double)__ldg(vv + e) : d);
+        red_add_f64(yh + u, HASVAL ? d * (double)__ldg(vv + e) : d);
       }
     }
   }
@@ -1795,7 +1802,7 @@ __global__ void __launch_bounds__(kClusterNT, kClusterCtasPerSm) cd_cluster_kern
       for (int64_t k = r0 + lane; k < r1; k += 32) {
         const int i = __ldg(a.rowind + k);
         const double prod = HASVAL ? (double)__ldg(a.rowval + k) * vy : 1.0;
-        atomicAdd(&acc[i], prod);
+        red_add_f64(&acc[i], prod);
       }
       if (lane == 0) expand += (r1 - r0);
     }

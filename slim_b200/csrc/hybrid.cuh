@@ -99,12 +99,6 @@ __device__ __forceinline__ void hyb_st_peer_int(int *local, uint32_t peer, int v
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
 }
 
-// fire-and-forget fp64 reduction (SASS REDG.E.ADD.F64): atomicAdd() with an unused result is compiled to a returning
-// ATOMG inside these loops, and a lane's next ATOMG waits for the previous one
-__device__ __forceinline__ void hyb_red_add(double *p, double v) {
-  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-
 // entries e_k = e0 + sub + G k, k < 16, of column range [.., s1): 16 id loads, then 16 yhat gathers in flight per lane
 template <bool HASVAL, int G>
 __device__ __forceinline__ double hyb_dot16(const SolveArgs &a, long long c0, int e0, int s1, int sub, const double *yh) {
@@ -139,7 +133,7 @@ __device__ __forceinline__ void hyb_axpy16(const SolveArgs &a, long long c0, int
   }
 #pragma unroll
   for (int k = 0; k < 16; k++)
-    if (id[k] >= 0) hyb_red_add(yh + id[k], HASVAL ? d * (double)vl[k] : d);
+    if (id[k] >= 0) red_add_f64(yh + id[k], HASVAL ? d * (double)vl[k] : d);
 }
 
 template <typename GA, bool HASVAL>
@@ -376,7 +370,7 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
           const int len = M.s1[m] - M.s0[m];
           if (d != 0.0)
             for (int k = tid >> 7; k < len; k += NT / BK)
-              hyb_red_add(yh + sm.sid[buf][k][m], HASVAL ? d * (double)sm.sval[HASVAL ? buf : 0][HASVAL ? k : 0][HASVAL ? m : 0] : d);
+              red_add_f64(yh + sm.sid[buf][k][m], HASVAL ? d * (double)sm.sval[HASVAL ? buf : 0][HASVAL ? k : 0][HASVAL ? m : 0] : d);
         }
       }
       if ((M.gmask[0] | M.gmask[1] | M.gmask[2] | M.gmask[3]) != 0u) {
