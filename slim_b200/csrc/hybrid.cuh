@@ -68,7 +68,7 @@ struct __align__(16) HybMeta {  // one block of active coordinates, as seen by t
 template <typename GA, bool HASVAL>
 struct __align__(16) HybSmem {
   float tile[2][kHybBK][kHybBK];  // G[block][block] (upper triangle used), double buffered
-  HybMeta<GA> meta[2];
+  HybMeta<GA> meta[3];            // ring: the block of this round, of the next round and of the round after
   int sid[2][kHybLane][kHybBK];                                      // user ids of the class-1 columns, read ahead
   float sval[HASVAL ? 2 : 1][HASVAL ? kHybLane : 1][HASVAL ? kHybBK : 1];  // ... and their values
   double mine[2][kHybBK];         // this CTA's partial inner products; peers read them through DSMEM
@@ -85,6 +85,15 @@ struct __align__(16) HybSmem {
 
 __device__ __forceinline__ void hyb_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void hyb_cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void hyb_cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void hyb_bar_warps03() {  // named barrier 1: the four warps that own the block's sums
+  asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 __device__ __forceinline__ double hyb_ld_peer(const double *local, uint32_t peer) {
   uint32_t ra;
@@ -134,6 +143,73 @@ __device__ __forceinline__ void hyb_axpy16(const SolveArgs &a, long long c0, int
 #pragma unroll
   for (int k = 0; k < 16; k++)
     if (id[k] >= 0) red_add_f64(yh + id[k], HASVAL ? d * (double)vl[k] : d);
+}
+
+// One warp over the entries e_begin + lane + 32 k + i * step of a LONG column range, software-pipelined: the user ids
+// of step i+1 are requested together with the yhat gathers of step i, so a step costs one load latency, not two.
+template <bool HASVAL>
+__device__ __forceinline__ double hyb_dot_range(const SolveArgs &a, long long c0, int e_begin, int s1, int step, int lane,
+                                                const double *yh) {
+  const int32_t *ix = a.colind + c0;
+  int id[16];
+  float vl[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int e = e_begin + lane + 32 * k;
+    id[k] = e < s1 ? __ldg(ix + e) : -1;
+    if (HASVAL) vl[k] = e < s1 ? __ldg(a.colval + c0 + e) : 0.f;
+  }
+  double acc = 0.0;
+  for (int e0 = e_begin; e0 < s1; e0 += step) {
+    double y[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) y[k] = __ldcg(yh + (id[k] < 0 ? 0 : id[k]));
+    int idn[16];
+    float vln[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int e = e0 + step + lane + 32 * k;
+      idn[k] = e < s1 ? __ldg(ix + e) : -1;
+      if (HASVAL) vln[k] = e < s1 ? __ldg(a.colval + c0 + e) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      acc += id[k] < 0 ? 0.0 : (HASVAL ? (double)vl[k] * y[k] : y[k]);
+      id[k] = idn[k];
+      if (HASVAL) vl[k] = vln[k];
+    }
+  }
+  return acc;
+}
+
+template <bool HASVAL>
+__device__ __forceinline__ void hyb_axpy_range(const SolveArgs &a, long long c0, int e_begin, int s1, int step, int lane,
+                                               double d, double *yh) {
+  const int32_t *ix = a.colind + c0;
+  int id[16];
+  float vl[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int e = e_begin + lane + 32 * k;
+    id[k] = e < s1 ? __ldg(ix + e) : -1;
+    if (HASVAL) vl[k] = e < s1 ? __ldg(a.colval + c0 + e) : 0.f;
+  }
+  for (int e0 = e_begin; e0 < s1; e0 += step) {
+    int idn[16];
+    float vln[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int e = e0 + step + lane + 32 * k;
+      idn[k] = e < s1 ? __ldg(ix + e) : -1;
+      if (HASVAL) vln[k] = e < s1 ? __ldg(a.colval + c0 + e) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      if (id[k] >= 0) red_add_f64(yh + id[k], HASVAL ? d * (double)vl[k] : d);
+      id[k] = idn[k];
+      if (HASVAL) vl[k] = vln[k];
+    }
+  }
 }
 
 template <typename GA, bool HASVAL>
@@ -251,14 +327,15 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
     const int maxit = (int)(cap64 < (long long)a.maxniters ? cap64 : (long long)a.maxniters);
     const int nblk = (na + BK - 1) / BK;
 
-    // Read-ahead of block `b` into buffer `nb`, every part ONE load latency deep:
-    //   prefetch_meta (warps 4-7, at the start of the previous round, before their share of the inner products):
-    //     the block's coordinate lines;
-    //   prefetch_ids (warps 4-7) and prefetch_tile (warps 1-3, 8-15), while warp 0 runs the previous block's chain:
-    //     the user ids of the short (class-1) column ranges and G[block][block] through the descriptors in shared memory.
-    auto prefetch_meta = [&](int b, int nb) {
+    // Read-ahead, every part ONE load latency deep, issued right after a round's partial sums are on their way and
+    // overlapped with the exchange and the chain of that round:
+    //   prefetch_meta (warps 4-7): the coordinate lines of the block TWO rounds ahead -> meta ring slot `ms`;
+    //   prefetch_ids (warps 4-7): user ids of the short (class-1) column ranges of the NEXT block (its meta slot was
+    //     filled a round earlier) -> id buffer `ts`;
+    //   prefetch_tile (warps 8-15): G[block][block] of the next block through the descriptors of its meta slot -> tile `ts`.
+    auto prefetch_meta = [&](int b, int ms) {
       if (warp < 4 || warp > 7) return;
-      HybMeta<GA> &M = sm.meta[nb];
+      HybMeta<GA> &M = sm.meta[ms];
       const int p0 = b * BK;
       const int n = min(BK, na - p0);
       const int m = tid - 128;
@@ -295,12 +372,11 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
         M.bmask[warp - 4] = b4;
         M.wmask[warp - 4] = b3;
         M.gmask[warp - 4] = b2;
-        sm.dep[nb][warp - 4] = 0u;
       }
     };
-    auto prefetch_ids = [&](int nb) {  // needs meta[nb]
+    auto prefetch_ids = [&](int ms, int nb) {
       if (warp < 4 || warp > 7) return;
-      const HybMeta<GA> &M = sm.meta[nb];
+      const HybMeta<GA> &M = sm.meta[ms];
       const int m = tid - 128;
       if (M.cls[m] == 1) {
         const long long c0 = M.c0[m];
@@ -319,18 +395,21 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
         }
       }
     };
-    auto prefetch_tile = [&](int b, int nb) {  // needs meta[nb]
-      if (warp == 0 || (warp >= 4 && warp <= 7)) return;
-      const HybMeta<GA> &M = sm.meta[nb];
+    auto prefetch_tile = [&](int b, int ms, int nb) {
+      if (warp < 8) return;
+      const HybMeta<GA> &M = sm.meta[ms];
       const int n = min(BK, na - b * BK);
       // the 8128 elements above the diagonal, flattened: rows P and 127 - P together hold exactly 127 of them
-      constexpr int NTH = (NW - 5) * 32, PER = (BK * (BK - 1) / 2 + NTH - 1) / NTH;
-      const int t = (warp < 4 ? warp - 1 : warp - 5) * 32 + lane;
+      constexpr int NTH = (NW - 8) * 32, PER = (BK * (BK - 1) / 2 + NTH - 1) / NTH;
+      const int t = (warp - 8) * 32 + lane;
       constexpr int HALF = PER / 2;
       static_assert(PER % 2 == 0, "two batches");
 #pragma unroll 1
       for (int k0 = 0; k0 < PER; k0 += HALF) {  // two batches of HALF independent gathers per lane
-        float v[HALF];
+        // Above the diagonal the row item is the more popular one (actives ascend), so the element is always stored
+        // as row r of column c, in both layouts.  Addresses first, then all loads, then the conversions: no branch
+        // between two loads, HALF of them in flight per lane.
+        uint32_t w[HALF];
 #pragma unroll
         for (int k = 0; k < HALF; k++) {
           const int e = t + (k0 + k) * NTH;
@@ -338,12 +417,11 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
           const bool top = o < BK - 1 - P;
           const int r = top ? P : BK - 1 - P;
           const int c = top ? P + 1 + o : BK - P + (o - (BK - 1 - P));
-          double g = 0.0;
-          if (e < BK * (BK - 1) / 2 && c < n) {
-            if constexpr (GA::kStair) g = GA::at(gv, M.dcol[r], M.dcol[c]);
-            else g = GA::at(gv, M.dcol[c], M.item[r]);
-          }
-          v[k] = (float)g;
+          const bool ok = e < BK * (BK - 1) / 2 && c < n;
+          const int cs_ = ok ? c : 0, rs_ = ok ? r : 0;
+          unsigned long long adr;
+          asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(adr) : "r"((uint32_t)M.item[rs_]), "r"((uint32_t)M.dcol[cs_].stride), "l"(M.dcol[cs_].p));
+          w[k] = ok ? __ldg(reinterpret_cast<const uint32_t *>(adr)) : 0u;
         }
 #pragma unroll
         for (int k = 0; k < HALF; k++) {
@@ -353,16 +431,17 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
           const int r = top ? P : BK - 1 - P;
           const int c = top ? P + 1 + o : BK - P + (o - (BK - 1 - P));
           if (e < BK * (BK - 1) / 2 && c < n) {
-            sm.tile[nb][r][c] = v[k];
-            if (v[k] != 0.f) atomicOr(&sm.dep[nb][r >> 5], 1u << (r & 31));
+            const uint32_t v = __byte_perm(w[k], 0u, M.dcol[c].sel);
+            sm.tile[nb][r][c] = (float)v;
+            if (v != 0u) atomicOr(&sm.dep[nb][r >> 5], 1u << (r & 31));
           }
         }
       }
     };
 
     // yhat slice += d * (this CTA's range of the block's columns), for the coordinates with d != 0
-    auto update_yhat = [&](int buf, int n) {
-      const HybMeta<GA> &M = sm.meta[buf];
+    auto update_yhat = [&](int ms, int buf, int n) {
+      const HybMeta<GA> &M = sm.meta[ms];
       {  // class 1: user ids staged in shared memory, one entry per thread and pass (4 entries of every column per pass)
         const int m = tid & (BK - 1);
         if (m < n && M.cls[m] == 1) {
@@ -388,7 +467,7 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
           if (M.cls[m] == 3) {
             const double d = sm.dlt[m];
             if (d != 0.0)
-              for (int e0 = M.s0[m]; e0 < M.s1[m]; e0 += 512) hyb_axpy16<HASVAL, 32>(a, M.c0[m], e0, M.s1[m], lane, d, yh);
+              hyb_axpy_range<HASVAL>(a, M.c0[m], M.s0[m], M.s1[m], 512, lane, d, yh);
           }
       }
 #pragma unroll
@@ -398,35 +477,38 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
           const int m = 32 * w4 + __ffs(mm) - 1;
           mm &= mm - 1;
           const double d = sm.dlt[m];
-          if (d != 0.0)
-            for (int e0 = M.s0[m] + warp * 512; e0 < M.s1[m]; e0 += NW * 512)
-              hyb_axpy16<HASVAL, 32>(a, M.c0[m], e0, M.s1[m], lane, d, yh);
+          if (d != 0.0) hyb_axpy_range<HASVAL>(a, M.c0[m], M.s0[m] + warp * 512, M.s1[m], NW * 512, lane, d, yh);
         }
       }
     };
 
-    int cur = 0;
+    int mc = 0, tc = 0;  // meta ring slot and tile / id buffer of the current block
+    if (tid < 8) sm.dep[tid >> 2][tid & 3] = 0u;
     // ---- warm start: yhat slice = sum_k x_k a_k over this CTA's user range -------------------------------
     if (warm) {
       for (int b = 0; b < nblk; b++) {
         const int p0 = b * BK, n = min(BK, na - p0);
-        prefetch_meta(b, cur);
+        prefetch_meta(b, mc);
         if (tid < BK) {
           const double xi = tid < n ? x[p0 + tid] : 0.0;
           sm.dlt[tid] = fabs(xi) > kEps ? xi : 0.0;
         }
         __syncthreads();
-        prefetch_ids(cur);
+        prefetch_ids(mc, tc);
         __syncthreads();
-        update_yhat(cur, n);
+        update_yhat(mc, tc, n);
         __syncthreads();
       }
     }
-    if (nblk > 0) prefetch_meta(0, cur);
+    if (nblk > 0) {
+      prefetch_meta(0, 0);
+      __syncthreads();  // (the same warps fill both slots)
+      prefetch_meta(nblk > 1 ? 1 : 0, 1);
+    }
     __syncthreads();
     if (nblk > 0) {
-      prefetch_ids(cur);
-      prefetch_tile(0, cur);
+      prefetch_ids(0, 0);
+      prefetch_tile(0, 0, 0);
     }
     __syncthreads();
 
@@ -439,15 +521,15 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
       for (; t < maxit && !done; t++) {
         double dl = 0.0;  // warp 0: this lane's share of sum (x' - x)^2
         for (int b = 0; b < nblk; b++) {
-          const HybMeta<GA> &M = sm.meta[cur];
+          const HybMeta<GA> &M = sm.meta[mc];
           const int p0 = b * BK, n = min(BK, na - p0);
-          const int bn = b + 1 == nblk ? 0 : b + 1;
+          const int bn1 = b + 1 == nblk ? 0 : b + 1, bn2 = bn1 + 1 == nblk ? 0 : bn1 + 1;
+          const int mn1 = mc == 2 ? 0 : mc + 1, mn2 = mn1 == 2 ? 0 : mn1 + 1, tn = tc ^ 1;
           const bool prof_on = ha.prof != nullptr && rank == 0 && tid == 0;
           const int pheavy = ((M.bmask[0] | M.bmask[1] | M.bmask[2] | M.bmask[3] | M.wmask[0] | M.wmask[1] | M.wmask[2] |
                                M.wmask[3]) != 0u) ? 4 : 0;
           long long pt0 = 0, pt1 = 0, pt2 = 0, pt3 = 0;
           if (prof_on) pt0 = clock64();
-          prefetch_meta(bn, cur ^ 1);
           double xv[4] = {0.0, 0.0, 0.0, 0.0};
           if (warp == 0) {
 #pragma unroll
@@ -461,10 +543,10 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
               const int len = M.s1[tid] - M.s0[tid];
               double y[kHybLane];
 #pragma unroll
-              for (int k = 0; k < kHybLane; k++) y[k] = k < len ? __ldcg(yh + sm.sid[cur][k][tid]) : 0.0;
+              for (int k = 0; k < kHybLane; k++) y[k] = k < len ? __ldcg(yh + sm.sid[tc][k][tid]) : 0.0;
 #pragma unroll
               for (int k = 0; k < kHybLane; k++)
-                v += HASVAL ? (double)sm.sval[HASVAL ? cur : 0][HASVAL ? k : 0][HASVAL ? tid : 0] * y[k] : y[k];
+                v += HASVAL ? (double)sm.sval[HASVAL ? tc : 0][HASVAL ? k : 0][HASVAL ? tid : 0] * y[k] : y[k];
             }
             sm.mine[xb][tid] = v;
           }
@@ -483,8 +565,7 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
           if ((M.wmask[0] | M.wmask[1] | M.wmask[2] | M.wmask[3]) != 0u) {
             for (int m = warp; m < n; m += NW)
               if (M.cls[m] == 3) {
-                double v = 0.0;
-                for (int e0 = M.s0[m]; e0 < M.s1[m]; e0 += 512) v += hyb_dot16<HASVAL, 32>(a, M.c0[m], e0, M.s1[m], lane, yh);
+                double v = hyb_dot_range<HASVAL>(a, M.c0[m], M.s0[m], M.s1[m], 512, lane, yh);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (lane == 0) sm.mine[xb][m] = v;
@@ -498,9 +579,7 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
               while (mm) {
                 const int m = 32 * w4 + __ffs(mm) - 1;
                 mm &= mm - 1;
-                double v = 0.0;
-                for (int e0 = M.s0[m] + warp * 512; e0 < M.s1[m]; e0 += NW * 512)
-                  v += hyb_dot16<HASVAL, 32>(a, M.c0[m], e0, M.s1[m], lane, yh);
+                double v = hyb_dot_range<HASVAL>(a, M.c0[m], M.s0[m] + warp * 512, M.s1[m], NW * 512, lane, yh);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (lane == 0) sm.pwb[warp][m] = v;
@@ -516,19 +595,23 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
           }
           // ---- sum over the CTAs of the cluster (rank order: bit-identical everywhere)
           if (prof_on) pt1 = clock64();
-          hyb_cluster_sync();
+          hyb_cluster_arrive();
+          prefetch_meta(bn2, mn2);
+          prefetch_ids(mn1, tn);
+          prefetch_tile(bn1, mn1, tn);
+          hyb_cluster_wait();
           if (tid < n) {
             double s = 0.0;
             for (int c = 0; c < cs; c++) s += hyb_ld_peer(&sm.mine[xb][tid], (uint32_t)c);
             sm.tot[tid] = s;
           }
           xb ^= 1u;
-          __syncthreads();
+          if (warp < 4) hyb_bar_warps03();
           if (prof_on) pt2 = clock64();
 
           if (warp == 0) {
             // ---- exact sequential CD inside the block (cd.c:117-133); only coordinates whose value changes are visited
-            const float(*T)[BK] = sm.tile[cur];
+            const float(*T)[BK] = sm.tile[tc];
             double ipf[4], xn[4], sq[4], den[4], aty[4];
             bool valid[4];
 #pragma unroll
@@ -548,7 +631,7 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
 #pragma unroll
             for (int s = 0; s < 4; s++) {
               if (32 * s >= n) break;
-              const unsigned em = sm.dep[cur][s];
+              const unsigned em = sm.dep[tc][s];
               int k = 0;
               for (;;) {
                 const double in_old = fabs(xn[s]) > kEps ? xn[s] : 0.0;
@@ -587,13 +670,11 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
               if (valid[s] && xn[s] != xv[s]) x[p0 + m] = xn[s];
               sm.dlt[m] = valid[s] ? now - was : 0.0;
             }
-          } else {
-            prefetch_ids(cur ^ 1);
-            prefetch_tile(bn, cur ^ 1);
           }
           __syncthreads();
           if (prof_on) pt3 = clock64();
-          update_yhat(cur, n);
+          if (tid < 4) sm.dep[tc][tid] = 0u;  // (free again: the gather of the round after the next one sets its bits)
+          update_yhat(mc, tc, n);
           __syncthreads();  // (yhat slices are private to a CTA: block-level visibility is all the next round needs)
           if (prof_on) {
             unsigned long long *pp = ha.prof + (size_t)q * 10;
@@ -603,7 +684,8 @@ __global__ void __launch_bounds__(kHybNT, 1) cd_hybrid_kernel(const SolveArgs a,
             pp[pheavy + 3] += (unsigned long long)(clock64() - pt3);
             pp[8 + (pheavy >> 2)] += 1ull;
           }
-          cur ^= 1;
+          mc = mn1;
+          tc = tn;
         }
         // ---- end of sweep: stop rule (cd.c:135-138)
         if (warp == 0) {
