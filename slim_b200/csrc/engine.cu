@@ -63,32 +63,80 @@ static inline void ck(cudaError_t e, const char *what) {
 }
 #define CK(x) ck((x), #x)
 
+// Temporary device buffers.  Inside an AsyncAllocScope (learn()) they come from the device's stream-ordered memory
+// pool (cudaMallocAsync / cudaFreeAsync on the engine stream, release threshold "never": no device-wide
+// synchronisation and no page (un)mapping per call -- cudaMalloc / cudaFree of the ~100 MB pools and sort buffers cost
+// 10-700 ms per learn() call on a device that holds a 13 GB Gram matrix); elsewhere plain cudaMalloc / cudaFree.
+static thread_local cudaStream_t t_alloc_stream = nullptr;
+static thread_local bool t_alloc_async = false;
+struct AsyncAllocScope {
+  bool prev_on;
+  cudaStream_t prev_s;
+  explicit AsyncAllocScope(cudaStream_t s) : prev_on(t_alloc_async), prev_s(t_alloc_stream) {
+    t_alloc_async = true;
+    t_alloc_stream = s;
+  }
+  AsyncAllocScope(const AsyncAllocScope &) = delete;
+  AsyncAllocScope &operator=(const AsyncAllocScope &) = delete;
+  ~AsyncAllocScope() {
+    t_alloc_async = prev_on;
+    t_alloc_stream = prev_s;
+  }
+};
+// *pooled = true when the memory came from the pool (free it with dev_free(.., true, stream) or with cudaFree)
+static cudaError_t dev_malloc(void **p, size_t bytes, bool *pooled) {
+  if (t_alloc_async) {
+    if (cudaMallocAsync(p, bytes, t_alloc_stream) == cudaSuccess) {
+      *pooled = true;
+      return cudaSuccess;
+    }
+    (void)cudaGetLastError();
+  }
+  *pooled = false;
+  return cudaMalloc(p, bytes);
+}
+static void dev_free(void *p, bool pooled, cudaStream_t s) {
+  if (!p) return;
+  if (pooled) {
+    if (cudaFreeAsync(p, s) == cudaSuccess) return;
+    (void)cudaGetLastError();
+  }
+  cudaFree(p);
+}
+
 template <class T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  bool pooled = false;
+  cudaStream_t pstream = nullptr;
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
   ~DevBuf() { reset(); }
   void reset() {
-    if (p) cudaFree(p);
+    dev_free(p, pooled, pstream);
     p = nullptr;
     n = 0;
+    pooled = false;
   }
   void alloc(size_t count) {
     reset();
     n = count;
-    CK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    pstream = t_alloc_stream;
+    void *q = nullptr;
+    CK(dev_malloc(&q, std::max<size_t>(count, 1) * sizeof(T), &pooled));
+    p = static_cast<T *>(q);
   }
   void alloc_zero(size_t count, cudaStream_t s) {
     alloc(count);
     CK(cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), s));
   }
-  T *release() {
+  T *release() {  // (the new owner frees with cudaFree, which accepts pool memory too)
     T *q = p;
     p = nullptr;
     n = 0;
+    pooled = false;
     return q;
   }
 };
@@ -536,6 +584,14 @@ Matrix *stage(int device, int32_t nrows, const ssize_t *rowptr, const int32_t *r
     m->sm_count = prop.multiProcessorCount;
     m->smem_optin = (int)prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    {  // the stream-ordered pool keeps what learn() frees (see DevBuf); build_gram() trims it before it sizes G
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      (void)cudaGetLastError();
+    }
     CK(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m->stream3, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m->stream4, cudaStreamNonBlocking));
@@ -2567,6 +2623,11 @@ static void build_gram(Matrix *m) {
   size_t bytes = packed ? off8 + ((ld - h16) / kGramPW) * nr * kGramPW + 16  // (+16: word loads at the very end)
                               : npan * nr * kGramPW * sizeof(double);
   size_t free_b = 0, total_b = 0;
+  {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, m->device) == cudaSuccess) (void)cudaMemPoolTrimTo(pool, 0);
+    (void)cudaGetLastError();
+  }
   CK(cudaMemGetInfo(&free_b, &total_b));
   // leave room for the solve scratch and the result pools
   const size_t reserve = std::min((size_t)16 << 30, total_b / 4);
@@ -3033,6 +3094,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     DeviceGuard guard(m->device);
     (void)cudaGetLastError();
     cudaStream_t s = m->stream;
+    AsyncAllocScope alloc_scope(s);  // temporaries of this call: stream-ordered pool (see DevBuf)
     const int32_t ncols = m->ncols, nrows = m->nrows;
     const int32_t nsel = cols ? nsel_in : ncols;
     if (nsel < 0) throw EngineError(kErrInput, "learn: negative column count");
@@ -3369,6 +3431,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     struct Pool {
       int32_t *idx;
       float *val;
+      bool pooled_idx, pooled_val;
     };
     std::vector<Pool> pools;
     std::vector<int32_t> pool_of(nsel, 0);
@@ -3376,8 +3439,8 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     double solve_ms = 0.0;
     auto free_pools = [&]() {
       for (auto &pl : pools) {
-        cudaFree(pl.idx);
-        cudaFree(pl.val);
+        dev_free(pl.idx, pl.pooled_idx, s);
+        dev_free(pl.val, pl.pooled_val, s);
       }
       pools.clear();
     };
@@ -3407,10 +3470,10 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
         d_ob.alloc(nt);
         d_ph.alloc_zero((size_t)nt * 4, s);
         d_ng.alloc_zero(nt, s);
-        Pool pl{nullptr, nullptr};
-        CK(cudaMalloc(&pl.idx, sizeof(int32_t) * cap));
+        Pool pl{nullptr, nullptr, false, false};
+        CK(dev_malloc(reinterpret_cast<void **>(&pl.idx), sizeof(int32_t) * cap, &pl.pooled_idx));
         pools.push_back(pl);
-        CK(cudaMalloc(&pools.back().val, sizeof(float) * cap));
+        CK(dev_malloc(reinterpret_cast<void **>(&pools.back().val), sizeof(float) * cap, &pools.back().pooled_val));
         CK(cudaMemcpyAsync(d_targets.p, tcols.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice, s));
         args.targets = d_targets.p;
         args.ntargets = nt;
@@ -3604,10 +3667,13 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
       // ---- ordered gather into compact CSC (caller's column order) ------------------------------
       for (int32_t q = 0; q < nsel; q++) res->h_colptr[q + 1] = res->h_colptr[q] + cnt[q];
       res->nnz = res->h_colptr[nsel];
-      CK(cudaMalloc(&res->d_colptr, sizeof(int64_t) * ((size_t)nsel + 1)));
-      CK(cudaMalloc(&res->d_counts, sizeof(int32_t) * std::max(nsel, 1)));
-      CK(cudaMalloc(&res->d_colind, sizeof(int32_t) * std::max<int64_t>(res->nnz, 1)));
-      CK(cudaMalloc(&res->d_colval, sizeof(float) * std::max<int64_t>(res->nnz, 1)));
+      {  // (pool memory as well; free_result() releases it with cudaFree, which accepts both kinds)
+        bool pooled_ignored = false;
+        CK(dev_malloc(reinterpret_cast<void **>(&res->d_colptr), sizeof(int64_t) * ((size_t)nsel + 1), &pooled_ignored));
+        CK(dev_malloc(reinterpret_cast<void **>(&res->d_counts), sizeof(int32_t) * std::max(nsel, 1), &pooled_ignored));
+        CK(dev_malloc(reinterpret_cast<void **>(&res->d_colind), sizeof(int32_t) * std::max<int64_t>(res->nnz, 1), &pooled_ignored));
+        CK(dev_malloc(reinterpret_cast<void **>(&res->d_colval), sizeof(float) * std::max<int64_t>(res->nnz, 1), &pooled_ignored));
+      }
       CK(cudaMemcpyAsync(res->d_colptr, res->h_colptr.data(), sizeof(int64_t) * ((size_t)nsel + 1),
                          cudaMemcpyHostToDevice, s));
       CK(cudaEventRecord(e1, s));

@@ -9,11 +9,15 @@
 //     kHybBK = 128 consecutive ACTIVE coordinates against the yhat at the start of the round; CTA r of the cluster
 //     owns user range r (colsplit) and with it a private slice of yhat;
 //   * the sequential dependence inside the block (cd.c:117-133 visits the coordinates one after the other) is
-//     resolved exactly with the 128 x 128 Gram tile G[block][block] -- 16 K gathered elements of the resident G, read
-//     ahead while the previous block's chain runs -- by one warp that only visits coordinates whose value changes;
-//   * yhat += d_i a_i (cd.c:129) for the coordinates that changed, fp64 reductions into the CTA's own slice.
-// A round costs one cluster barrier per 128 active coordinates; inactive items cost nothing.  Iterates, stop rule,
-// cap and compaction are those of the other kernels (estimate.c:433-505).
+//     resolved exactly with the 128 x 128 Gram tile G[block][block] -- 8 K gathered elements of the resident G above
+//     the diagonal, read ahead while the previous block's sums are exchanged and its chain runs -- by one warp that
+//     only visits the coordinates whose value changes AND whose tile row is not zero ("emitters");
+//   * yhat += d_i a_i (cd.c:129) for the coordinates that changed, fp64 reductions (REDG) into the CTA's own slice.
+// A round costs one cluster barrier per 128 active coordinates (~10 us for short column ranges, measured with
+// SLIMB200_PROFILE=1: profiles/r02_c5_hybrid_notes.txt); inactive items cost nothing.  Iterates, stop rule, cap and
+// compaction are those of the other kernels (estimate.c:433-505).
+// Timestamps of the profile: BAR.SYNC is compiled DEFER_BLOCKING, so a clock read right after __syncthreads() can
+// precede the barrier's completion -- the wait then shows up in the NEXT interval.
 #pragma once
 
 constexpr int kHybNT = 512;
