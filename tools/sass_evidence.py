@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """SASS evidence for profiles/: per kernel of slim_b200/lib/libslim.so, the count of the instructions that show
 which hardware paths the kernel uses (TMA bulk copies UBLKCP, cp.async LDGSTS, mbarrier SYNCS, DSMEM MAPA + cluster
-stores, cluster barriers UCGABAR, fp64 tensor-core DMMA, fp64 FMA, reductions RED / atomics ATOM) plus one sample
+stores and generic LD.E loads of peer shared memory, cluster barriers UCGABAR (split: UCGABAR_ARV / UCGABAR_WAIT), fp64 tensor-core DMMA, fp64 FMA, reductions RED / atomics ATOM) plus one sample
 line of each.  Runs anywhere (cuobjdump only reads the ELF):   python tools/sass_evidence.py > profiles/rNN_sass_evidence.txt
 """
 import collections
@@ -11,7 +11,7 @@ import sys
 from pathlib import Path
 
 LIB = Path(__file__).resolve().parent.parent / "slim_b200" / "lib" / "libslim.so"
-KEYS = ["UBLKCP", "LDGSTS", "LDGDEPBAR", "SYNCS", "MAPA", "UCGABAR", "DMMA", "DFMA", "HMMA", "UTCMMA", "RED", "REDG", "ATOM", "ATOMG", "PRMT",
+KEYS = ["UBLKCP", "LDGSTS", "LDGDEPBAR", "SYNCS", "MAPA", "UCGABAR", "UCGABAR_ARV", "UCGABAR_WAIT", "LD.E", "DMMA", "DFMA", "HMMA", "UTCMMA", "RED", "REDG", "ATOM", "ATOMG", "PRMT",
         "I2F.F64", "SHFL", "BAR.SYNC", "LDG", "LDS", "STS", "ST.E"]
 
 
@@ -29,7 +29,9 @@ def main():
     print(f"# cuobjdump -sass {LIB.name}: instruction counts per kernel (static), sm_100a")
     want = sys.argv[1:] or ["cd_gram_batch_kernel<slimb200::GaPacked, 16, 8, 2, 512, true>", "cd_gram_batch_kernel<slimb200::GaPacked, 16, 8, 2, 512, false>",
                             "cd_gram_kernel<slimb200::GaPacked, 4>", "cd_gram_kernel<slimb200::GaPacked, 1>",
-                            "gram_build_kernel<slimb200::GbPacked, false>", "cd_cluster_kernel<false, true>",
+                            "cd_gram_kernel<slimb200::GaStair, 1", "cd_hybrid_kernel<slimb200::GaStair, false>",
+                            "gram_build_kernel<slimb200::GbPacked, false>", "gram_build_kernel<slimb200::GbStair, false>",
+                            "cd_cluster_kernel<false, true>",
                             "cd_solve_kernel<128, true, false>", "fslim_neighbors_kernel<false>", "predict_topn_kernel",
                             "place_columns_kernel", "fill_rows_kernel"]
     for fn, ins in body.items():
