@@ -3157,13 +3157,15 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
     if (cs != 0 && cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) cs = 16;
     // GIANT targets next to a resident packed Gram matrix: in the STAIR layout (build_gram) a Gram-space sweep of a
     // target with >= ~5 000 nonzeros gathers |S| x |A| ~ 10^9 scattered elements, more than the nnz(R) entries a
-    // user-space sweep streams, so those targets go to cd_hybrid_kernel (hybrid.cuh: user-space inner products, exact
+    // user-space sweep streams, so the heaviest targets go to cd_hybrid_kernel (from 9 000 nonzeros: the 16-CTA
+    // clusters of the hybrid kernel are the scarce resource of a step, the one-target Gram clusters fill the other
+    // SMs; 4 096-column C5 steps: 5 721 / 5 278 / 5 112 / 5 628 ms for thresholds 5 000 / 7 000 / 9 000 / 12 000) (hybrid.cuh: user-space inner products, exact
     // block solve with Gram tiles), launched side by side with the Gram classes.  SLIMB200_STAIR_USER sets the
     // threshold for the stair layout, SLIMB200_HYBRID_MIN for any packed layout (default: never for the full layout,
     // where the batched kernel is faster); SLIMB200_GIANT_KERNEL=cluster runs them on cd_cluster_kernel instead.
     const bool stair = use_gram && m->gram_stair;
     const int stair_user = (use_gram && !m->gram_f64 && !fslim)
-                               ? env_int("SLIMB200_HYBRID_MIN", stair ? env_int("SLIMB200_STAIR_USER", 5000) : INT32_MAX)
+                               ? env_int("SLIMB200_HYBRID_MIN", stair ? env_int("SLIMB200_STAIR_USER", 9000) : INT32_MAX)
                                : INT32_MAX;
     int32_t n_user = 0;
     if (stair_user != INT32_MAX)
