@@ -70,7 +70,8 @@ int32_t SLIMB200_MatrixGramStair(const slimb200_matrix_t *matrix, int32_t *stair
 
 /* Solve target columns cols[0..ncols_sel) (cols == NULL: every column): the per-column body of
  * EstimateModelCD (reference src/libslim/estimate.c:405-505) + CoordinateDescent (cd.c:101-142).
- * Options as for SLIM_Learn.  imodel: optional warm-start model handle. */
+ * Options as for SLIM_Learn.  imodel: optional warm-start model handle.  Calls on DIFFERENT staged matrices run
+ * concurrently; concurrent calls on the same matrix are serialised inside the library (its solve scratch is per matrix). */
 slimb200_result_t *SLIMB200_LearnColumns(slimb200_matrix_t *matrix, const int32_t *ioptions,
                                          const double *doptions, const int32_t *cols,
                                          int32_t ncols_sel, const slim_t *imodel, int32_t *r_status);

@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <stdexcept>
 #include <string>
@@ -246,6 +247,8 @@ struct Matrix {
   // solve scratch, cached between learn() calls on the same matrix
   void *d_scratch = nullptr;
   size_t scratch_bytes = 0;
+  // learn() keeps per-call state here (scratch, the class streams): concurrent calls on ONE staged matrix are serialised
+  std::mutex learn_mutex;
 };
 
 void free_matrix(Matrix *m) {
@@ -3091,6 +3094,7 @@ Result *learn(Matrix *m, const LearnParams &p, const int32_t *cols, int32_t nsel
   const double w_start = wall();
   double w_plan = 0, w_solved = 0, w_gathered = 0;
   try {
+    std::lock_guard<std::mutex> one_call_at_a_time(m->learn_mutex);
     DeviceGuard guard(m->device);
     (void)cudaGetLastError();
     cudaStream_t s = m->stream;
